@@ -1,0 +1,114 @@
+// omg_hier.cuh — host-side hierarchy object (levels, vectors, cached CUDA graphs).
+#pragma once
+#include <map>
+#include <tuple>
+
+#include "omg_common.cuh"
+
+struct Globals {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // halo / copy stream
+    // distributed state (omg_dist.cu)
+    int rank = 0, nranks = 1;
+    void *nccl_comm = nullptr;
+};
+extern Globals g;
+
+struct Level {
+    // geometry
+    int n = 0;                 // global rows
+    int row0 = 0;              // first owned global row (0 on one GPU)
+    int nloc = 0;              // owned rows
+    int pad = 0;               // zero pad / halo width on each side (multiple of 16)
+    int ndim = 0;
+    int shape[3] = {1, 1, 1};  // level shape, openmg/operators.py:131,136 (C order, as given)
+    ColourRule colour{};
+
+    // operator
+    int kind = OMG_KIND_CSR;
+    BandOp band{};
+    int64_t nexc = 0;
+    unsigned *exc_mask = nullptr;
+    int *exc_wpre = nullptr, *exc_ptr = nullptr, *exc_col = nullptr;
+    double *exc_val = nullptr, *exc_diag = nullptr;
+    // full CSR (sorted columns, global indices == local on one GPU); may be absent for a band level 0
+    int64_t nnz = 0;
+    int *ptr = nullptr, *col = nullptr;
+    double *val = nullptr, *diag = nullptr;
+
+    // restriction to level+1
+    bool hasR = false;
+    bool regular = false;
+    RegR reg{};
+    int Rk = 0;                // entries per R row (after dedupe)
+    int Roffs[8] = {0};
+    double Rw = 0.0;
+    int nc = 0;                // rows of R (= n of next level)
+    int *Rptr = nullptr, *Rcol = nullptr, *RTptr = nullptr, *RTcol = nullptr;   // explicit pattern (non-regular)
+    int *Rcc = nullptr;        // explicit: first column per coarse row
+
+    // vectors [pad | nloc | pad]
+    double *xa_base = nullptr, *xb_base = nullptr, *b_base = nullptr, *r_base = nullptr;
+    double *xa = nullptr, *xb = nullptr, *b = nullptr, *r = nullptr;
+
+    ExcOp exc_op() const { return ExcOp{exc_mask, exc_wpre, exc_ptr, exc_col, exc_val, exc_diag}; }
+    CsrOp csr_op() const { return CsrOp{ptr, col, val, diag}; }
+};
+
+struct CycleCfg {
+    int pre, post, smoother, with_norm;
+    double omega;
+    int cur0;   // which level-0 buffer holds the iterate on entry
+    bool operator<(const CycleCfg &o) const {
+        return std::tie(pre, post, smoother, with_norm, omega, cur0) <
+               std::tie(o.pre, o.post, o.smoother, o.with_norm, o.omega, o.cur0);
+    }
+};
+
+struct CachedGraph {
+    cudaGraphExec_t exec = nullptr;
+    int cur0_after = 0;
+    int64_t launches = 0;
+};
+
+struct omg_hierarchy {
+    int flags = 0;
+    int nlev = 0;
+    std::vector<Level> lv;
+    std::vector<void *> allocs;      // everything cudaMalloc'ed for this hierarchy
+    // coarse solve
+    double *Ainv = nullptr;
+    int ncoarse = 0;
+    // norm reduction scratch
+    double *partial = nullptr;
+    int npartial = 0;
+    double *norm2_dev = nullptr;     // device scalar: sum of squares
+    double *norm2_host = nullptr;    // pinned
+    // state
+    int cur0 = 0;                    // level-0 iterate lives in xa (0) or xb (1)
+    std::map<CycleCfg, CachedGraph> graphs;
+    int64_t launches = 0;            // kernels launched since last reset
+    // timings
+    double t_upload_ms = 0, t_galerkin_ms = 0, t_coarse_ms = 0;
+};
+
+// allocation helpers (omg_setup.cu)
+int h_alloc(omg_hierarchy *h, void **p, size_t bytes, bool zero);
+template <class T>
+static inline int h_alloc_t(omg_hierarchy *h, T **p, size_t count, bool zero = false) {
+    return h_alloc(h, (void **)p, count * sizeof(T), zero);
+}
+void h_free(omg_hierarchy *h, void *p);
+
+int exclusive_scan_i32(const int *in, int *out, int n, int *total_host, cudaStream_t st);
+
+// omg_setup.cu
+int setup_levels(omg_hierarchy *h, int ndim, const int64_t *shape, int coarsestLevel, int minSize);
+int build_hierarchy(omg_hierarchy *h);
+int materialize_level_csr(omg_hierarchy *h, const Level &L, int **ptr, int **col, double **val, int64_t *nnz);
+
+// omg_cycle.cu
+int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);

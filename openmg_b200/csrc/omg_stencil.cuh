@@ -1,0 +1,13 @@
+// omg_stencil.cuh — structured fast paths (constant 1-D/2-D/3-D band stencils with the
+// closed-form restriction).  Each function returns false when the level does not match
+// its preconditions; the caller then launches the generic kernel of omg_kernels.cuh.
+#pragma once
+#include "omg_hier.cuh"
+
+// xo = xi + omega (b - A xi)/diag
+bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega);
+// rc = R (b - A x)
+bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *x, const double *b, double *rc);
+// y = xi + R^T e ; xo = y + omega (b - A y)/diag      (prolong + correct + first post-smoothing sweep)
+bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
+                            const double *b, double *xo, double omega);
