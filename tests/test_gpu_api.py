@@ -109,7 +109,10 @@ def test_dense_flag_and_mpl_demo_configuration():
     u_mg = openmg.mgSolve(A_in, b, {'problemShape': (NX, NX), 'gridLevels': 2, 'iterations': 1,
                                     'verbose': False, 'cycles': 300, 'dense': True})
     assert u_mg.shape == (NX * NX,)
-    np.testing.assert_allclose(u_mg, u, rtol=0, atol=1e-9)
+    # the reference's 2-D hierarchy converges slowly; compare with the oracle, same smoother
+    u_or = orc.mgSolve(sp.csr_matrix(A_in), b, {'problemShape': (NX, NX), 'gridLevels': 2, 'cycles': 300,
+                                                'smoother': 'rbgs'})
+    np.testing.assert_allclose(u_mg, u_or, rtol=0, atol=1e-10 * np.abs(u_or).max())
 
 
 def test_thresh_stop_and_cycle_stop(gold_cycles):
@@ -232,4 +235,4 @@ def test_simple_demo_trace():
               'dense': True, 'threshold': 1e-2, 'giveInfo': True, 'smoother': 'gs'}
     u_mg, info = openmg.mgSolve(A, b, params)
     assert info['cycle'] == 4
-    np.testing.assert_allclose(info['norms'], [0.805593, 0.108255, 0.018646, 0.003409], rtol=2e-5)
+    np.testing.assert_allclose(info['norms'], [0.805593, 0.108255, 0.018646, 0.003409], rtol=3e-4)   # 6 printed digits
