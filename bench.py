@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — V-cycle throughput of the openmg hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--shape 512 512 512] [--grid-levels 5] [--smoother jacobi|rbgs]
+                    [--pre 1] [--post 1]
+
+Workload (BASELINE.json configs[3]): 3-D Poisson 512^3 (openmg's generator: diag -12,
++1 at +-1, +-NX, +-NX*NY), fp64, gridLevels=5 -> 6 grids (coarsest 16^3), V(1,1),
+u = RandomState(0).random_sample(N), b = A u, zero initial iterate.
+A "step" is one V-cycle.  `value` = DOF*cycles/s with b resident in HBM (CUDA events on
+the library stream, max over ranks); `e2e` = the same metric through the public call
+(Hierarchy.solve -> omg_solve) from pinned HOST buffers, host<->device copies inside the
+timed region.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dof_cycles_per_s"
+UNIT = "DOF*cycles/s"
+
+
+def algorithmic_bytes_per_cycle(sizes, pre, post, with_norm=False):
+    """SURVEY.md §8(d) / BASELINE.md §3: compulsory fp64 vector traffic of one fused V(pre,post)."""
+    B = 0.0
+    L = len(sizes) - 1
+    for l in range(L):
+        n, nc = sizes[l], sizes[l + 1]
+        B += 24.0 * pre * n - (8.0 * n if (l >= 1 and pre >= 1) else 0.0)
+        B += 16.0 * n + 8.0 * nc
+        B += 8.0 * nc + (24.0 * post * n if post >= 1 else 16.0 * n)
+    B += 16.0 * sizes[L]
+    if with_norm:
+        B += 16.0 * sizes[0]
+    return B
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.idx = device_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    f = [s.strip() for s in line.split(",")]
+                    if len(f) >= 9:
+                        self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, name in enumerate(names):
+                if s[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(s[3]) for s in self.samples if s[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def problem(shape, s1):
+    import openmg_b200 as omg
+    return omg.operators.poisson_band(shape, sparse_1d=s1)
+
+
+def dist_setup(ngpus):
+    """torchrun plumbing: returns (rank, world, barrier, allreduce_max)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world == 1:
+        return 0, 1, (lambda: None), (lambda v: v), None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return rank, world, barrier, allmax, dist
+
+
+# ---------------------------------------------------------------------------------- CPU legs
+
+def cpu_port_rate(shape, gl, pre, post, smoother, budget_s=20.0):
+    """The oracle's vectorised scipy restatement of the SAME cycle (same smoother) on the host,
+    one thread, on a bounded sample of the workload (a smaller cube, same depth rule)."""
+    import oracle.openmg_oracle as orc
+    s = len(shape)
+    sample = {3: (256, 256, 256), 2: (4096, 4096), 1: (1 << 24,)}[s]
+    sample = tuple(min(a, b) for a, b in zip(sample, shape))
+    A0 = orc.poisson_csr(sample, sparse_1d=(s == 1))
+    N = A0.shape[0]
+    u = np.random.RandomState(0).random_sample(N)
+    b = A0.dot(u)
+    t0 = time.perf_counter()
+    R = orc.restrictionList(sample, gl - 1, 8)
+    A = orc.coeffecientList(A0, R)
+    setup_s = time.perf_counter() - t0
+    params = {'coarsestLevel': len(R), 'preIterations': pre, 'postIterations': post, 'verbose': False}
+    smooth = orc.make_smoother(smoother, sample, 0.8)
+    x = None
+    cycles = 0
+    t0 = time.perf_counter()
+    while True:
+        x, info = orc.mgCycle(A, b, 0, R, params, initial=x, smooth=smooth)
+        cycles += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or cycles >= 8:
+            break
+    rate = N * cycles / el
+    return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle (scipy CSR, vectorised %s) V(%d,%d) on %s, %d grids, %d cycles in %.1f s "
+                      "(+%.1f s setup), host has %d cores"
+                      % (smoother, pre, post, "x".join(map(str, sample)), len(A), cycles, el, setup_s,
+                         os.cpu_count())}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own algorithm as-is (lexicographic Gauss-Seidel in a
+    Python loop over CSR rows, openmg/solvers.py:34-75; SuperLU coarse solve every cycle) through
+    the oracle port (the reference is Python 2 and does not exist on the GPU box), on a bounded
+    sample of the workload."""
+    import oracle.openmg_oracle as orc
+    shape = tuple(args.shape)
+    s = len(shape)
+    sample = {3: (24, 24, 24), 2: (128, 128), 1: (1 << 14,)}[s]
+    sample = tuple(min(a, b) for a, b in zip(sample, shape))
+    A0 = orc.poisson_csr(sample, sparse_1d=(s == 1))
+    N = A0.shape[0]
+    u = np.random.RandomState(0).random_sample(N)
+    b = A0.dot(u)
+    R = orc.restrictionList(sample, args.grid_levels - 1, 8)
+    A = orc.coeffecientList(A0, R)
+    params = {'coarsestLevel': len(R), 'preIterations': args.pre, 'postIterations': args.post, 'verbose': False}
+    smooth = orc.make_smoother('gs', sample, fast=False)          # the literal Python row loop
+    x = None
+    for _ in range(min(args.warmup, 1)):
+        x, _i = orc.mgCycle(A, b, 0, R, params, initial=x, smooth=smooth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x, _i = orc.mgCycle(A, b, 0, R, params, initial=x, smooth=smooth)
+    el = time.perf_counter() - t0
+    rate = N * args.steps / el
+    port = cpu_port_rate(shape, args.grid_levels, args.pre, args.post, args.smoother, budget_s=10.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vcycles_per_s": args.steps / el,
+        "config": {"workload": "3-D Poisson %s fp64, gridLevels=%d, V(%d,%d)" % (
+            "x".join(map(str, shape)), args.grid_levels, args.pre, args.post),
+            "sample": "x".join(map(str, sample)), "grids": len(A), "smoother": "lexicographic GS (reference as-is)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "reference algorithm as-is (pure-Python lexicographic GS row loop + spsolve) on "
+                                   "%s, %d grids, %d cycles; single thread by construction; host has %d cores"
+                                   % ("x".join(map(str, sample)), len(A), args.steps, os.cpu_count())},
+        "cpu_port_same_smoother": port,
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- our arm
+
+def ours(args):
+    rank, world, barrier, allmax, dist = dist_setup(args.gpus)
+    import openmg_b200 as omg
+    from openmg_b200 import _lib
+    from openmg_b200.hierarchy import Hierarchy
+
+    shape = tuple(args.shape)
+    s1 = len(shape) == 1
+    if world > 1:
+        from openmg_b200 import dist as omg_dist
+        omg_dist.init_from_torch(dist)
+    dev = _lib.device_info()
+    A = problem(shape, s1)
+    N = A.n
+    t0 = time.perf_counter()
+    h = Hierarchy(A, shape, args.grid_levels - 1, 8)
+    setup_wall = time.perf_counter() - t0
+    nlev = h.nlevels
+    sizes = [h.level_info(l)["n"] for l in range(nlev)]
+    kinds = [h.level_info(l)["kind"] for l in range(nlev)]
+
+    # synthetic input: u uniform[0,1), b = A u; computed on the device from host u
+    u = np.random.RandomState(0).random_sample(N)
+    b_host = _lib.pinned_empty(N)
+    b_host[:] = h.matvec(u, 0)
+    x_host = _lib.pinned_empty(N)
+    h.set_rhs(b_host)
+
+    # ---- device-resident timing: W warm-up cycles, then exactly K timed cycles
+    h.bench_cycles(max(args.warmup, 3), args.pre, args.post, args.smoother, 0.8)
+    barrier()
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as cs:
+        ms, launches = h.bench_cycles(args.steps, args.pre, args.post, args.smoother, 0.8)
+        barrier()
+        # keep the sampler alive for at least a few samples on short runs
+        if ms < 600:
+            ms2, _ = h.bench_cycles(max(args.steps, int(600 / max(ms / args.steps, 1e-3))), args.pre, args.post,
+                                    args.smoother, 0.8)
+    ms = allmax(ms)
+    clocks = cs.summary()
+    final_norm = h.current_norm()
+    value = N * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel shares (CUDA events, direct launches) and the roofline of the dominant kernel
+    prof = h.profile_cycle(3, args.pre, args.post, args.smoother, 0.8)
+    tot = sum(p["ms"] * p["launches"] / 3.0 for p in prof)
+    dom = max(prof, key=lambda p: p["ms"] * p["launches"])
+    peak, peak_src = peaks()
+    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+    Bcyc = algorithmic_bytes_per_cycle(sizes, args.pre, args.post)
+    cyc_ach = Bcyc / (ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "%s@L%d" % (dom["name"], dom["level"]), "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_cycle": dom["ms"] * dom["launches"] / 3.0 / tot if tot > 0 else None}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get(dom["name"] + "@L%d" % dom["level"])
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- end to end through the public call with HOST buffers (pinned), copies inside the timed region
+    cyc_call = args.e2e_cycles
+    h.solve(b_host, None, args.pre, args.post, args.smoother, 0.8, 1, 0.0, out=x_host)       # warm
+    barrier()
+    ncalls = max(1, args.steps // cyc_call)
+    t0 = time.perf_counter()
+    for _ in range(ncalls):
+        x_host, done, norm, _h = h.solve(b_host, None, args.pre, args.post, args.smoother, 0.8, cyc_call, 0.0,
+                                         out=x_host)
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e = {"value": N * cyc_call * ncalls / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": 8.0 * N / world / cyc_call, "d2h_bytes_per_step": 8.0 * N / world / cyc_call,
+           "cycles_per_call": cyc_call, "calls": ncalls, "ms_per_call": 1e3 * e2e_s / ncalls,
+           "call": "openmg_b200.Hierarchy.solve -> omg_solve (pinned host b in, host x out, final residual norm read)",
+           "final_norm": norm}
+
+    if rank != 0:
+        return
+    cpu = cpu_port_rate(shape, args.grid_levels, args.pre, args.post, args.smoother) if world == 1 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vcycles_per_s": args.steps / (ms * 1e-3),
+        "config": {"workload": "3-D Poisson %s fp64 (openmg generator), gridLevels=%d -> %d grids %s, V(%d,%d) %s, "
+                               "omega=0.8, b=A*u u~U[0,1) seed 0, zero initial iterate" % (
+                                   "x".join(map(str, shape)), args.grid_levels, nlev, sizes, args.pre, args.post,
+                                   args.smoother),
+                   "level_kinds": kinds, "l2_policy": "inputs larger than L2 (3 x %.2f GB level-0 vectors)" % (8e-9 * N),
+                   "parallelism": "slab%d" % world, "device": dev["name"]},
+        "roofline": roofline,
+        "cycle_roofline": {"algorithmic_bytes_per_cycle": Bcyc, "achieved": cyc_ach, "unit": "GB/s",
+                           "frac_of_measured_peak": cyc_ach / peak, "frac_of_8TBs_nominal": cyc_ach / 8000.0},
+        "kernels": [{"kernel": "%s@L%d" % (p["name"], p["level"]), "launches_per_cycle": p["launches"] / 3.0,
+                     "ms": p["ms"], "GBs": p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else None}
+                    for p in prof],
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "setup": dict(h.setup_times(), wall_s=setup_wall), "final_norm_after_timed_cycles": final_norm,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", type=int, nargs="+", default=[512, 512, 512])
+    ap.add_argument("--grid-levels", type=int, default=5)
+    ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "rbgs"])
+    ap.add_argument("--pre", type=int, default=1)
+    ap.add_argument("--post", type=int, default=1)
+    ap.add_argument("--e2e-cycles", type=int, default=10)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        reference_arm(args)
+        return 0
+    ours(args)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -163,6 +163,11 @@ int omg_cycle(omg_hierarchy *h, int level, const double *b_host, double *x_host,
 int omg_set_rhs(omg_hierarchy *h, const double *b_host);
 int omg_bench_cycles(omg_hierarchy *h, int pre, int post, int smoother, double omega,
                      int ncycles, int with_norm, float *ms, int64_t *launches);
+/* Per-kernel CUDA-event timing of `reps` V-cycles launched directly (no graph) on the rhs set
+ * by omg_set_rhs: JSON array of {"name","level","launches","ms" (avg per launch),"bytes"
+ * (algorithmic bytes per launch)} written to json[cap]. */
+int omg_profile_cycle(omg_hierarchy *h, int pre, int post, int smoother, double omega, int reps,
+                      char *json, int cap);
 int omg_get_solution(omg_hierarchy *h, double *x_host);
 int omg_current_norm(omg_hierarchy *h, double *norm);
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "omg_set_rhs": (ctypes.c_int, [c_h, c_f64p]),
     "omg_bench_cycles": (ctypes.c_int, [c_h, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_i64p]),
+    "omg_profile_cycle": (ctypes.c_int, [c_h, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "omg_get_solution": (ctypes.c_int, [c_h, c_f64p]),
     "omg_current_norm": (ctypes.c_int, [c_h, c_f64p]),
     "omg_smooth": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, ctypes.c_int, ctypes.c_int,

@@ -567,6 +567,65 @@ int omg_bench_cycles(omg_hierarchy *h, int pre, int post, int smoother, double o
     return OMG_OK;
 }
 
+// Per-kernel CUDA-event timing of `reps` cycles launched directly (no graph): writes a JSON
+// array [{"name":..,"level":..,"launches":..,"ms":avg per launch,"bytes":algorithmic per launch},..]
+int omg_profile_cycle(omg_hierarchy *h, int pre, int post, int smoother, double omega, int reps, char *json,
+                      int cap) {
+    CHECK_H(h);
+    OMG_TRY(check_cfg(pre, post, smoother, omega));
+    if (reps <= 0 || !json || cap < 64) return omg_set_error(OMG_EINVAL, "bad arguments to omg_profile_cycle");
+    CycleCfg cfg{pre, post, smoother, 0, omega, 0};
+    OMG_TRY(upload_state(h, nullptr, nullptr, 0));
+    OMG_TRY(run_cycle(h, cfg));   // warm
+    OMG_TRY(run_cycle(h, cfg));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    h->profiling = true;
+    h->prof.clear();
+    int rc = OMG_OK;
+    for (int r = 0; r < reps && rc == OMG_OK; ++r) {
+        cfg.cur0 = h->cur0;
+        rc = run_cycle(h, cfg);
+    }
+    h->profiling = false;
+    cudaError_t e = cudaStreamSynchronize(g.stream);
+    struct Agg {
+        const char *name;
+        int level;
+        int n;
+        double ms, bytes;
+    };
+    std::vector<Agg> agg;
+    for (auto &r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        bool found = false;
+        for (auto &a : agg)
+            if (a.level == r.level && strcmp(a.name, r.name) == 0) {
+                a.n++;
+                a.ms += ms;
+                found = true;
+                break;
+            }
+        if (!found) agg.push_back(Agg{r.name, r.level, 1, ms, r.bytes});
+    }
+    h->prof.clear();
+    if (rc != OMG_OK) return rc;
+    if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "profile failed: %s", cudaGetErrorString(e));
+    std::string out = "[";
+    for (size_t i = 0; i < agg.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"level\":%d,\"launches\":%d,\"ms\":%.6f,\"bytes\":%.0f}",
+                 i ? "," : "", agg[i].name, agg[i].level, agg[i].n, agg[i].ms / agg[i].n, agg[i].bytes);
+        out += buf;
+    }
+    out += "]";
+    if ((int)out.size() + 1 > cap) return omg_set_error(OMG_EINVAL, "profile buffer too small");
+    memcpy(json, out.c_str(), out.size() + 1);
+    return OMG_OK;
+}
+
 int omg_get_solution(omg_hierarchy *h, double *x_host) {
     CHECK_H(h);
     return download_x(h, x_host);

@@ -30,14 +30,17 @@
     } while (0)
 
 static inline double *other(Level &L, double *cur) { return cur == L.xa ? L.xb : L.xa; }
+static inline int lvl(omg_hierarchy *h, const Level &L) { return (int)(&L - h->lv.data()); }
 
 int launch_matvec(omg_hierarchy *h, Level &L, const double *x, double *y) {
+    ProfScope ps(h, "matvec", lvl(h, L), 16.0 * L.nloc);
     DISPATCH_A(L, (k_matvec<decltype(A)><<<GRID(L.nloc)>>>(A, 0, L.nloc, x, y)));
     h->launches++;
     return OMG_OK;
 }
 
 int launch_residual(omg_hierarchy *h, Level &L, const double *x, const double *b, double *r) {
+    ProfScope ps(h, "residual", lvl(h, L), 24.0 * L.nloc);
     DISPATCH_A(L, (k_residual<decltype(A)><<<GRID(L.nloc)>>>(A, 0, L.nloc, x, b, r)));
     h->launches++;
     return OMG_OK;
@@ -47,6 +50,7 @@ int launch_residual(omg_hierarchy *h, Level &L, const double *x, const double *b
 int launch_resnorm2(omg_hierarchy *h, Level &L, const double *x, const double *b, int slot) {
     int blocks = std::min(h->npartial, cdiv(L.nloc, OMG_TPB));
     blocks = std::max(blocks, 1);
+    ProfScope ps(h, "residual_norm", lvl(h, L), 16.0 * L.nloc);
     DISPATCH_A(L, (k_resnorm_partial<decltype(A)><<<blocks, OMG_TPB, 0, g.stream>>>(A, 0, L.nloc, x, b, h->partial)));
     k_final_sum<<<1, 1024, 0, g.stream>>>(h->partial, blocks, h->norm2_dev + slot);
     h->launches += 2;
@@ -65,9 +69,11 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
     if (smoother == OMG_SMOOTH_JACOBI) {
         for (int s = 0; s < sweeps; ++s) {
             if (cur == nullptr) {
+                ProfScope ps(h, "jacobi_zero", lvl(h, L), 16.0 * n);
                 DISPATCH_A(L, (k_jacobi_zero<decltype(A)><<<GRID(n)>>>(A, 0, n, b, L.xa, omega)));
                 cur = L.xa;
             } else {
+                ProfScope ps(h, "jacobi", lvl(h, L), 24.0 * n);
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_jacobi(h, L, cur, b, out, omega)) {
                 } else {
@@ -80,6 +86,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
     } else if (smoother == OMG_SMOOTH_RBGS) {
         for (int s = 0; s < sweeps; ++s)
             for (int c = 0; c < 2; ++c) {
+                ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n);
                 double *out = other(L, cur);
                 DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, L.row0, 0, n, cur, b, out)));
                 cur = out;
@@ -87,6 +94,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
             }
     } else {   // lexicographic GS, in place
         if (sweeps > 0) {
+            ProfScope ps(h, "lexgs", lvl(h, L), 24.0 * n * sweeps);
             DISPATCH_A(L, (k_lexgs<decltype(A)><<<1, 32, 0, g.stream>>>(A, n, cur, b, sweeps)));
             h->launches++;
         }
@@ -99,6 +107,7 @@ int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const dou
     Level &L = h->lv[l];
     Level &C = h->lv[l + 1];
     if (L.regular) {
+        ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * C.nloc);
         if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_residual_restrict(h, L, C, x, b, rc)) {
         } else {
             DISPATCH_A(L, (k_residual_restrict<decltype(A)><<<GRID(C.nloc)>>>(A, L.reg, C.row0, L.row0, 0, C.nloc, x, b, rc)));
@@ -110,6 +119,7 @@ int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const dou
             L.r = L.r_base;
         }
         launch_residual(h, L, x, b, L.r);
+        ProfScope ps(h, "restrict", l, 8.0 * L.nloc + 8.0 * C.nloc);
         k_restrict_explicit<<<GRID(C.nloc)>>>(L.Rcc, L.reg, 0, C.nloc, L.r, rc);
         h->launches++;
     }
@@ -120,6 +130,7 @@ int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const dou
 int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const double *xi, double *xo) {
     Level &L = h->lv[l];
     Level &C = h->lv[l + 1];
+    ProfScope ps(h, "prolong_correct", l, 16.0 * L.nloc + 8.0 * C.nloc);
     if (L.regular)
         k_prolong_correct<<<GRID(L.nloc)>>>(L.reg, C.row0, L.row0, 0, L.nloc, e, xi, xo);
     else
@@ -134,7 +145,18 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
     Level &L = h->lv[l];
     if (sweeps > 0 && smoother == OMG_SMOOTH_JACOBI && L.regular && !(h->flags & OMG_FLAG_NO_FUSED)) {
         double *out = other(L, cur);
-        if (stencil_prolong_jacobi(h, L, h->lv[l + 1], cur, e, b, out, omega)) {
+        bool ok;
+        {
+            ProfScope ps(h, "prolong_jacobi", l, 24.0 * L.nloc + 8.0 * h->lv[l + 1].nloc);
+            ok = stencil_prolong_jacobi(h, L, h->lv[l + 1], cur, e, b, out, omega);
+            if (!ok && ps.idx >= 0) {   // not applicable: drop the record
+                cudaEventDestroy(h->prof.back().e0);
+                cudaEventDestroy(h->prof.back().e1);
+                h->prof.pop_back();
+                ps.idx = -1;
+            }
+        }
+        if (ok) {
             h->launches++;
             return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
         }
@@ -146,6 +168,7 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
 
 int launch_coarse_solve(omg_hierarchy *h, const double *b, double *x) {
     int n = h->ncoarse;
+    ProfScope ps(h, "coarse_solve", h->nlev - 1, 16.0 * n);
     int blocks = n <= 512 ? 1 : std::min(cdiv((int64_t)n * 32, OMG_TPB), std::max(g.sm_count, 1) * 4);
     k_coarse_gemv<<<blocks, OMG_TPB, 0, g.stream>>>(h->Ainv, n, b, x);
     h->launches++;

@@ -74,8 +74,17 @@ struct CachedGraph {
     int64_t launches = 0;
 };
 
+struct ProfRec {
+    const char *name;
+    int level;
+    double bytes;       // algorithmic bytes of this launch
+    cudaEvent_t e0, e1;
+};
+
 struct omg_hierarchy {
     int flags = 0;
+    bool profiling = false;          // per-kernel CUDA-event timing (omg_profile_cycle)
+    std::vector<ProfRec> prof;
     int nlev = 0;
     std::vector<Level> lv;
     std::vector<void *> allocs;      // everything cudaMalloc'ed for this hierarchy
@@ -112,3 +121,21 @@ int materialize_level_csr(omg_hierarchy *h, const Level &L, int **ptr, int **col
 
 // omg_cycle.cu
 int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);
+
+// RAII event pair around one launch when h->profiling
+struct ProfScope {
+    omg_hierarchy *h;
+    int idx;
+    ProfScope(omg_hierarchy *h_, const char *name, int level, double bytes) : h(h_), idx(-1) {
+        if (!h->profiling) return;
+        ProfRec r{name, level, bytes, nullptr, nullptr};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, g.stream);
+        h->prof.push_back(r);
+        idx = (int)h->prof.size() - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(h->prof[idx].e1, g.stream);
+    }
+};

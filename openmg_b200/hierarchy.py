@@ -287,6 +287,14 @@ class Hierarchy(_Handle):
                                        1 if with_norm else 0, ctypes.byref(ms), ctypes.byref(launches)))
         return ms.value, launches.value
 
+    def profile_cycle(self, reps=3, pre=1, post=1, smoother="jacobi", omega=0.8):
+        """Per-kernel CUDA-event timings (list of dicts) of direct-launched cycles."""
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(self._L.omg_profile_cycle(self._h, int(pre), int(post), SMOOTHERS[smoother], float(omega), int(reps),
+                                        buf, 1 << 16))
+        return json.loads(buf.value.decode())
+
     def solution(self):
         x = np.empty(self.n(0), np.float64)
         check(self._L.omg_get_solution(self._h, f64(x)))
