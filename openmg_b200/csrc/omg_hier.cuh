@@ -34,6 +34,9 @@ struct Level {
     unsigned *exc_mask = nullptr;
     int *exc_wpre = nullptr, *exc_ptr = nullptr, *exc_col = nullptr;
     double *exc_val = nullptr, *exc_diag = nullptr;
+    int *exc_rows = nullptr;     // row index per exception slot
+    int *exc_crows = nullptr;    // coarse rows whose aggregate contains an exception row (regular R)
+    int nexc_crows = 0;
     // full CSR (sorted columns, global indices == local on one GPU); may be absent for a band level 0
     int64_t nnz = 0;
     int *ptr = nullptr, *col = nullptr;

@@ -661,6 +661,25 @@ __global__ void __launch_bounds__(OMG_TPB) k_exc_fill(const int *__restrict__ ro
     ediag[s] = d;
 }
 
+// global coarse row of every exception row -> bit mask over coarse rows (global index - 0 on one GPU)
+__global__ void k_mark_crows(const int *__restrict__ rows, int nexc, RegR R, int frow0, unsigned *__restrict__ cmask) {
+    int s = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (s >= nexc) return;
+    int I = reg_agg(R, rows[s] + frow0);
+    atomicOr(cmask + (I >> 5), 1u << (I & 31));
+}
+__global__ void k_popc_words(const unsigned *__restrict__ mask, int nw, int *__restrict__ cnt) {
+    int w = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (w < nw) cnt[w] = __popc(mask[w]);
+}
+__global__ void k_compact_bits(const unsigned *__restrict__ mask, const int *__restrict__ wpre, int n,
+                               int *__restrict__ out) {
+    int i = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i >= n) return;
+    unsigned w = mask[i >> 5];
+    if ((w >> (i & 31)) & 1u) out[wpre[i >> 5] + __popc(w & ((1u << (i & 31)) - 1u))] = i;
+}
+
 static int detect_band(omg_hierarchy *h, Level &L) {
     L.kind = OMG_KIND_CSR;
     if (h->flags & OMG_FLAG_FORCE_CSR) return OMG_OK;
@@ -747,11 +766,29 @@ static int detect_band(omg_hierarchy *h, Level &L) {
     k_exc_fill<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(rows, nexc, L.ptr, L.col, L.val, eptr, L.row0,
                                                               L.exc_col, L.exc_val, L.exc_diag);
     CUDA_TRY(cudaStreamSynchronize(g.stream));
-    h_free(h, rows);
+    L.exc_rows = rows;
     L.exc_mask = mask;
     L.exc_wpre = wpre;
     L.exc_ptr = eptr;
     L.kind = OMG_KIND_BAND_EXC;
+    // coarse rows touched by exception rows (fix-up list of the fused residual+restriction)
+    if (L.hasR && L.regular) {
+        int ncw = (L.nc + 31) / 32;
+        unsigned *cmask = nullptr;
+        int *cpre = nullptr;
+        OMG_TRY(h_alloc_t(h, &cmask, (size_t)ncw + 1, true));
+        OMG_TRY(h_alloc_t(h, &cpre, (size_t)ncw + 1, true));
+        k_mark_crows<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(rows, nexc, L.reg, L.row0, cmask);
+        k_popc_words<<<cdiv(ncw, OMG_TPB), OMG_TPB, 0, g.stream>>>(cmask, ncw, cpre);
+        int ncr = 0;
+        OMG_TRY(exclusive_scan_i32(cpre, cpre, ncw + 1, &ncr, g.stream));
+        OMG_TRY(h_alloc_t(h, &L.exc_crows, (size_t)std::max(ncr, 1)));
+        k_compact_bits<<<cdiv(L.nc, OMG_TPB), OMG_TPB, 0, g.stream>>>(cmask, cpre, L.nc, L.exc_crows);
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        L.nexc_crows = ncr;
+        h_free(h, cmask);
+        h_free(h, cpre);
+    }
     return OMG_OK;
 }
 
@@ -937,7 +974,7 @@ static int alloc_vectors(omg_hierarchy *h) {
         int reach = 0;
         if (L.kind != OMG_KIND_CSR)
             for (int k = 0; k < L.band.nb; ++k) reach = std::max(reach, std::abs(L.band.off[k]));
-        L.pad = (reach + 15) / 16 * 16;
+        L.pad = (2 * reach + 15) / 16 * 16;    // the 2.5-D stencil path stages plane -1 with its halo rows
         size_t len = (size_t)L.pad * 2 + (size_t)L.nloc + 16;
         OMG_TRY(h_alloc_t(h, &L.xa_base, len, true));
         OMG_TRY(h_alloc_t(h, &L.xb_base, len, true));
