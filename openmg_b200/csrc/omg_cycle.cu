@@ -169,7 +169,7 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
 int launch_coarse_solve(omg_hierarchy *h, const double *b, double *x) {
     int n = h->ncoarse;
     ProfScope ps(h, "coarse_solve", h->nlev - 1, 16.0 * n);
-    int blocks = n <= 512 ? 1 : std::min(cdiv((int64_t)n * 32, OMG_TPB), std::max(g.sm_count, 1) * 4);
+    int blocks = n <= 512 ? 1 : std::min(cdiv((int64_t)n * 32, OMG_TPB), std::max(g.sm_count, 1) * 8);
     k_coarse_gemv<<<blocks, OMG_TPB, 0, g.stream>>>(h->Ainv, n, b, x);
     h->launches++;
     return OMG_OK;
@@ -181,9 +181,27 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
         launch_coarse_solve(h, L.b, L.xa);
         return L.xa;
     }
-    cur = launch_smooth(h, L, cfg.smoother, cfg.omega, cfg.pre, cur, L.b);
     Level &C = h->lv[l + 1];
-    launch_residual_restrict(h, l, cur, L.b, C.b);
+    bool fused0 = false;
+    if (cur == nullptr && cfg.pre == 1 && cfg.smoother == OMG_SMOOTH_JACOBI && L.regular &&
+        !(h->flags & OMG_FLAG_NO_FUSED)) {
+        // zero initial iterate (openmg/__init__.py:191-192): sweep + residual + restriction in one pass over b
+        ProfScope ps(h, "jacobi0_residual_restrict", l, 16.0 * L.nloc + 8.0 * C.nloc);
+        fused0 = stencil_jacobi0_residual_restrict(h, L, C, L.b, L.xa, C.b, cfg.omega);
+        if (fused0) {
+            cur = L.xa;
+            h->launches++;
+        } else if (ps.idx >= 0) {
+            cudaEventDestroy(h->prof.back().e0);
+            cudaEventDestroy(h->prof.back().e1);
+            h->prof.pop_back();
+            ps.idx = -1;
+        }
+    }
+    if (!fused0) {
+        cur = launch_smooth(h, L, cfg.smoother, cfg.omega, cfg.pre, cur, L.b);
+        launch_residual_restrict(h, l, cur, L.b, C.b);
+    }
     double *e = cycle_level(h, l + 1, cfg, nullptr);
     return launch_prolong_correct_smooth(h, l, cfg.smoother, cfg.omega, cfg.post, cur, e, L.b);
 }

@@ -270,9 +270,8 @@ static __global__ void k_final_sum(const double *__restrict__ partial, int m, do
 
 // ---------------------------------------------------------------- coarse solve
 
-// x = Ainv b, dense row-major n x n inverse computed at setup: one warp per row.
-// Launched with one CTA when the inverse fits L1/L2-resident single-SM streaming
-// (n <= 512), otherwise across all SMs.
+// x = Ainv b, dense row-major n x n inverse computed at setup: one warp per row, 128-bit loads,
+// four independent accumulators (2 KB in flight per warp).  One CTA when n <= 512, else all SMs.
 static __global__ void __launch_bounds__(OMG_TPB) k_coarse_gemv(const double *__restrict__ Ainv, int n,
                                                          const double *__restrict__ b, double *__restrict__ x) {
     int warp = (blockIdx.x * OMG_TPB + threadIdx.x) >> 5;
@@ -280,9 +279,36 @@ static __global__ void __launch_bounds__(OMG_TPB) k_coarse_gemv(const double *__
     int nwarps = (gridDim.x * OMG_TPB) >> 5;
     for (int r = warp; r < n; r += nwarps) {
         const double *row = Ainv + (size_t)r * n;
-        double acc = 0.0;
-        for (int c = lane; c < n; c += 32) acc += __ldg(row + c) * __ldg(b + c);
-        acc = warp_sum(acc);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int c = 0;
+        if ((n & 1) == 0) {
+            const double2 *row2 = reinterpret_cast<const double2 *>(row);
+            const double2 *b2 = reinterpret_cast<const double2 *>(b);
+            int n2 = n >> 1;
+            int c2 = lane;
+            for (; c2 + 96 < n2; c2 += 128) {
+                double2 m0 = __ldg(row2 + c2), m1 = __ldg(row2 + c2 + 32), m2 = __ldg(row2 + c2 + 64),
+                        m3 = __ldg(row2 + c2 + 96);
+                double2 v0 = __ldg(b2 + c2), v1 = __ldg(b2 + c2 + 32), v2 = __ldg(b2 + c2 + 64),
+                        v3 = __ldg(b2 + c2 + 96);
+                a0 += m0.x * v0.x;
+                a0 += m0.y * v0.y;
+                a1 += m1.x * v1.x;
+                a1 += m1.y * v1.y;
+                a2 += m2.x * v2.x;
+                a2 += m2.y * v2.y;
+                a3 += m3.x * v3.x;
+                a3 += m3.y * v3.y;
+            }
+            for (; c2 < n2; c2 += 32) {
+                double2 m0 = __ldg(row2 + c2), v0 = __ldg(b2 + c2);
+                a0 += m0.x * v0.x;
+                a0 += m0.y * v0.y;
+            }
+            c = n;
+        }
+        for (c += lane; c < n; c += 32) a0 += __ldg(row + c) * __ldg(b + c);
+        double acc = warp_sum((a0 + a1) + (a2 + a3));
         if (lane == 0) x[r] = acc;
     }
 }

@@ -680,6 +680,11 @@ __global__ void k_compact_bits(const unsigned *__restrict__ mask, const int *__r
     if ((w >> (i & 31)) & 1u) out[wpre[i >> 5] + __popc(w & ((1u << (i & 31)) - 1u))] = i;
 }
 
+__global__ void k_diag_differs(const double *__restrict__ ediag, int nexc, double d, int *__restrict__ flag) {
+    int s = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (s < nexc && ediag[s] != d) *flag = 1;
+}
+
 static int detect_band(omg_hierarchy *h, Level &L) {
     L.kind = OMG_KIND_CSR;
     if (h->flags & OMG_FLAG_FORCE_CSR) return OMG_OK;
@@ -765,7 +770,16 @@ static int detect_band(omg_hierarchy *h, Level &L) {
     OMG_TRY(h_alloc_t(h, &L.exc_diag, (size_t)nexc));
     k_exc_fill<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(rows, nexc, L.ptr, L.col, L.val, eptr, L.row0,
                                                               L.exc_col, L.exc_val, L.exc_diag);
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    {   // are all exception diagonals equal to the stencil diagonal? (true for the Poisson hierarchies)
+        int *flag = nullptr;
+        OMG_TRY(h_alloc_t(h, &flag, 1, true));
+        k_diag_differs<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_diag, nexc, band.diag, flag);
+        int f = 0;
+        CUDA_TRY(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        L.exc_diag_uniform = (f == 0);
+        h_free(h, flag);
+    }
     L.exc_rows = rows;
     L.exc_mask = mask;
     L.exc_wpre = wpre;

@@ -8,34 +8,44 @@
 //    z-segment and marches along z.  Because rows are full, the chunk plus its +-S1 halo rows is
 //    ONE contiguous span of the flat vector per plane, so each plane is staged into shared
 //    memory by a single TMA bulk copy (cp.async.bulk.shared.global, SASS UBLKCP) completing on
-//    an mbarrier; a ring of NS spans keeps planes z-1, z, z+1 resident and 2 more in flight.
+//    an mbarrier; a ring of NS spans keeps planes z-1, z, z+1 resident and the rest in flight.
 //    The zero pads of the vectors make the global ends branch-free.
 //  * Each thread owns 2x2 (x,y) patches: all 7 taps are shared-memory reads (LDS.128 for the
 //    aligned pairs), b streams through ld.global.nc, results leave as 128-bit stores.
-//  * The fused residual+restriction accumulates the 2x2 patch over two planes in registers and
+//  * MODE 1 (residual+restriction) accumulates the 2x2 patch over two planes in registers and
 //    writes one coarse value: the fine residual never exists in HBM.
+//  * MODE 2 (prolong+correct+Jacobi) and MODE 3 (first Jacobi sweep from zero + residual +
+//    restriction) transform each staged plane in place in shared memory when it lands
+//    (y = x + w e[agg], resp. x = omega b / a_ii), so the 7-point pass itself is unchanged.
 //  * Rows deviating from the stencil ("exception rows" of Galerkin levels) are recomputed from
 //    their compact CSR by a small fix-up kernel right after (out-of-place, so still exact).
+#include <stdlib.h>
+
 #include "omg_stencil.cuh"
 #include "omg_kernels.cuh"
 
-#define ST_NT 512          // threads per CTA
 #define ST_PPT 2           // 2x2 patches per thread per plane (max)
-#define ST_NS 5            // ring stages
+#define ST_TPT 6           // span pairs per thread in the in-smem transform (max)
+#define ST_MAXNS 6
 
 struct St3 {
-    const double *xi;      // owned row 0 of the input vector (zero/halo padded)
+    const double *xi;      // staged vector: owned row 0 (zero/halo padded).  MODE 3: this is b.
     const double *b;
-    double *xo;            // fine output (jacobi) or coarse output (residual+restrict)
-    const double *e;       // coarse correction (prolong+jacobi)
+    double *xo;            // fine output (MODE 0,2: new iterate; MODE 3: x = omega b/diag)
+    double *rc;            // coarse output (MODE 1,3)
+    const double *e;       // coarse correction (MODE 2)
+    ExcOp exc;             // exception rows (MODE 3 needs their a_ii)
+    int has_exc;
+    int nloc;
     int S1, S2, NZ;        // row length, plane size, local planes
     int TY, NP, SPAN;      // rows per chunk, patches per plane-chunk, span length (TY+2)*S1
+    int NS;                // ring stages
     int ZL;                // planes per z-segment (even)
     int cs1, cs2;          // coarse rows per plane, coarse row length
     int NYg;               // rows per plane
-    int zg0, NZg;          // global index of local plane 0, global planes (prolong validity)
+    int zg0, NZg;          // global index of local plane 0, global planes
     int cz0;               // global index of local coarse plane 0
-    double d, c1, cS, cP, wod, w;   // wod = omega/d
+    double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,16 +78,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void sts2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 // MODE 0: xo = xi + omega (b - A xi)/d
 // MODE 1: rc = R (b - A xi)
 // MODE 2: y = xi + R^T e ; xo = y + omega (b - A y)/d
-template <int MODE>
-__global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
+// MODE 3: xo = omega b/diag (first Jacobi sweep from x = 0) ; rc = R (b - A xo)      [xi == b]
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ST_NS * P.SPAN * sizeof(double));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)P.NS * P.SPAN * sizeof(double));
+    constexpr bool XF = (MODE == 2 || MODE == 3);
+    const int NS = P.NS;
     const int tid = threadIdx.x;
     const int z0 = blockIdx.y * P.ZL;
     const int z1 = min(z0 + P.ZL, P.NZ);
@@ -86,13 +100,13 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
     const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
 
     if (tid == 0) {
-        for (int s = 0; s < ST_NS; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        for (int k = 0; k < ST_NS; ++k) {
+        for (int k = 0; k < NS; ++k) {
             int p = z0 - 1 + k;
             if (p > z1) break;
             mbar_expect_tx(full + k, span_bytes);
@@ -100,13 +114,13 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
         }
     }
 
-    // fixed patch assignment
+    // fixed 2x2 patch assignment
     const int HX = P.S1 >> 1;
     int px[ST_PPT], py[ST_PPT];
     bool act[ST_PPT];
 #pragma unroll
     for (int k = 0; k < ST_PPT; ++k) {
-        int p = tid + k * ST_NT;
+        int p = tid + k * NT;
         act[k] = p < P.NP;
         p = act[k] ? p : 0;
         py[k] = p / HX;
@@ -115,6 +129,94 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
     double acc[ST_PPT];
 #pragma unroll
     for (int k = 0; k < ST_PPT; ++k) acc[k] = 0.0;
+
+    // fixed span-pair assignment of the in-smem transform
+    int tq[ST_TPT], tx[ST_TPT];
+    bool tact[ST_TPT];
+    double aux[ST_TPT];        // MODE 2: e of the pair's coarse cell
+    unsigned auxm[ST_TPT];     // MODE 3: exception mask word of the pair
+    if (XF) {
+#pragma unroll
+        for (int k = 0; k < ST_TPT; ++k) {
+            int t = tid + k * NT;
+            tact[k] = 2 * t < P.SPAN;
+            t = tact[k] ? t : 0;
+            tq[k] = (2 * t) / P.S1;
+            tx[k] = 2 * t - tq[k] * P.S1;
+            aux[k] = 0.0;
+            auxm[k] = 0u;
+        }
+    }
+    // aux of local plane p for pair k
+    auto load_aux = [&](int p) {
+#pragma unroll
+        for (int k = 0; k < ST_TPT; ++k) {
+            if (!tact[k]) continue;
+            if (MODE == 2) {
+                int yy = y0 - 1 + tq[k];
+                int zz = p + P.zg0;
+                if (yy < 0) {              // flat-index wrap into the neighbouring plane
+                    yy = P.NYg - 1;
+                    zz -= 1;
+                } else if (yy >= P.NYg) {
+                    yy = 0;
+                    zz += 1;
+                }
+                double v = 0.0;
+                if (zz >= 0 && zz < P.NZg)
+                    v = __ldg(P.e + ((long long)((zz >> 1) - P.cz0) * P.cs1 + (yy >> 1)) * P.cs2 + (tx[k] >> 1));
+                aux[k] = v;
+            } else if (MODE == 3) {
+                unsigned m = 0u;
+                if (P.has_exc) {
+                    long long gl = (long long)p * P.S2 + span0 + (long long)tq[k] * P.S1 + tx[k];
+                    if (gl >= 0 && gl < P.nloc) m = __ldg(P.exc.mask + (gl >> 5));
+                }
+                auxm[k] = m;
+            }
+        }
+    };
+    auto transform = [&](int slot, int p) {
+        double *sp_ = stage + (size_t)slot * P.SPAN;
+#pragma unroll
+        for (int k = 0; k < ST_TPT; ++k) {
+            if (!tact[k]) continue;
+            int o = tq[k] * P.S1 + tx[k];
+            double2 v = lds2(sp_ + o);
+            if (MODE == 2) {
+                v.x += P.w * aux[k];
+                v.y += P.w * aux[k];
+            } else {
+                double s0 = P.wod, s1 = P.wod;
+                if (P.has_exc) {
+                    unsigned m = auxm[k];
+                    long long gl = (long long)p * P.S2 + span0 + o;
+                    int bit = (int)(gl & 31);
+                    if ((m >> bit) & 3u) {
+                        int base = __ldg(P.exc.wpre + (gl >> 5));
+                        if ((m >> bit) & 1u)
+                            s0 = P.omega / __ldg(P.exc.diag + base + __popc(m & ((1u << bit) - 1u)));
+                        if ((m >> (bit + 1)) & 1u)
+                            s1 = P.omega / __ldg(P.exc.diag + base + __popc(m & ((2u << bit) - 1u)));
+                    }
+                }
+                v.x *= s0;
+                v.y *= s1;
+            }
+            sts2(sp_ + o, v);
+        }
+    };
+
+    if (XF) {
+        // planes z0-1 and z0 are transformed up front, z0+1 inside the loop
+        load_aux(z0 - 1);
+        mbar_wait(full + 0, 0);
+        transform(0, z0 - 1);
+        load_aux(z0);
+        mbar_wait(full + 1, 0);
+        transform(1, z0);
+        load_aux(z0 + 1);
+    }
 
     for (int z = z0; z < z1; ++z) {
         const int q = z - (z0 - 1);                // ring position of plane z (plane z0-1 is 0)
@@ -128,17 +230,22 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
                 bb[k] = ldg2(P.b + gi + P.S1);
             }
         }
-        if (z == z0) {
+        if (!XF && z == z0) {
             mbar_wait(full + 0, 0);
             mbar_wait(full + 1, 0);
         }
         {
             int qq = q + 1;
-            mbar_wait(full + (qq % ST_NS), (uint32_t)((qq / ST_NS) & 1));
+            mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
+            if (XF) {
+                transform(qq % NS, z + 1);
+                if (z + 2 <= z1) load_aux(z + 2);
+                __syncthreads();
+            }
         }
-        const double *sm = stage + (size_t)((q - 1) % ST_NS) * P.SPAN;
-        const double *sc = stage + (size_t)(q % ST_NS) * P.SPAN;
-        const double *sp = stage + (size_t)((q + 1) % ST_NS) * P.SPAN;
+        const double *sm = stage + (size_t)((q - 1) % NS) * P.SPAN;
+        const double *sc = stage + (size_t)(q % NS) * P.SPAN;
+        const double *sp = stage + (size_t)((q + 1) % NS) * P.SPAN;
 #pragma unroll
         for (int k = 0; k < ST_PPT; ++k) {
             if (!act[k]) continue;
@@ -149,57 +256,12 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
             double2 ma = lds2(sm + oa), mb = lds2(sm + ob);
             double2 pa = lds2(sp + oa), pb = lds2(sp + ob);
             double la = sc[oa - 1], ra = sc[oa + 2], lb = sc[ob - 1], rb = sc[ob + 2];
-            if (MODE == 2) {
-                // y = x + w e[agg]: add the coarse correction to every tap (flat-index neighbours)
-                const int Y = (y0 >> 1) + py[k];                         // coarse row in plane
-                const int zg = z + P.zg0;                                // global fine plane
-                const int Zc = (zg >> 1) - P.cz0;                        // local coarse plane of z
-                const double *ec = P.e + ((long long)Zc * P.cs1 + Y) * P.cs2;
-                const double w = P.w;
-                // rows a and b (same coarse row), centre and in-row neighbours
-                const int X = px[k];
-                double e0 = __ldg(ec + X);
-                // north row ya-1: flat row index rho-1 (may fall into the previous plane)
-                const int ya = y0 + 2 * py[k];
-                double en = 0.0, es = 0.0, enl = 0.0, esr = 0.0;
-                {
-                    // row ya-1: same plane, or the last row of plane zg-1 (flat-index wrap)
-                    int zn = ya > 0 ? zg : zg - 1;
-                    int yn = ya > 0 ? ya - 1 : P.NYg - 1;
-                    if (zn >= 0) {
-                        const double *er = P.e + ((long long)((zn >> 1) - P.cz0) * P.cs1 + (yn >> 1)) * P.cs2;
-                        en = __ldg(er + X);
-                        enl = __ldg(er + P.cs2 - 1);
-                    }
-                    // row yb+1 = ya+2: same plane, or the first row of plane zg+1
-                    int zs = ya + 2 < P.NYg ? zg : zg + 1;
-                    int ys = ya + 2 < P.NYg ? ya + 2 : 0;
-                    if (zs < P.NZg) {
-                        const double *er = P.e + ((long long)((zs >> 1) - P.cz0) * P.cs1 + (ys >> 1)) * P.cs2;
-                        es = __ldg(er + X);
-                        esr = __ldg(er + 0);
-                    }
-                }
-                // left/right neighbours: same coarse row unless at the row ends (flat wrap)
-                double ela = (X > 0) ? __ldg(ec + X - 1) : enl;            // left of (ya, x=0) is (ya-1, S1-1)
-                double elb = (X > 0) ? ela : __ldg(ec + P.cs2 - 1);        // left of (yb, x=0) is (ya, S1-1)
-                double erb = (X < P.cs2 - 1) ? __ldg(ec + X + 1) : esr;    // right of (yb, S1-1) is (yb+1, 0)
-                double era = (X < P.cs2 - 1) ? erb : __ldg(ec + 0);        // right of (ya, S1-1) is (yb, 0)
-                // z neighbours
-                double em = 0.0, ep = 0.0;
-                if (zg - 1 >= 0) em = __ldg(P.e + ((long long)(((zg - 1) >> 1) - P.cz0) * P.cs1 + Y) * P.cs2 + X);
-                if (zg + 1 < P.NZg) ep = __ldg(P.e + ((long long)(((zg + 1) >> 1) - P.cz0) * P.cs1 + Y) * P.cs2 + X);
-                va.x += w * e0; va.y += w * e0; vb.x += w * e0; vb.y += w * e0;
-                vn.x += w * en; vn.y += w * en; vs.x += w * es; vs.y += w * es;
-                ma.x += w * em; ma.y += w * em; mb.x += w * em; mb.y += w * em;
-                pa.x += w * ep; pa.y += w * ep; pb.x += w * ep; pb.y += w * ep;
-                la += w * ela; lb += w * elb; ra += w * era; rb += w * erb;
-            }
             double ax0 = P.d * va.x + P.c1 * (la + va.y) + P.cS * (vn.x + vb.x) + P.cP * (ma.x + pa.x);
             double ax1 = P.d * va.y + P.c1 * (va.x + ra) + P.cS * (vn.y + vb.y) + P.cP * (ma.y + pa.y);
             double ax2 = P.d * vb.x + P.c1 * (lb + vb.y) + P.cS * (va.x + vs.x) + P.cP * (mb.x + pb.x);
             double ax3 = P.d * vb.y + P.c1 * (vb.x + rb) + P.cS * (va.y + vs.y) + P.cP * (mb.y + pb.y);
-            if (MODE == 1) {
+            const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
+            if (MODE == 1 || MODE == 3) {
                 double a = acc[k];
                 a += ba[k].x - ax0;
                 a += ba[k].y - ax1;
@@ -207,12 +269,15 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
                 a += bb[k].y - ax3;
                 if (z & 1) {
                     int Z = z >> 1;
-                    P.xo[((long long)Z * P.cs1 + (y0 >> 1) + py[k]) * P.cs2 + px[k]] = P.w * a;
+                    P.rc[((long long)Z * P.cs1 + (y0 >> 1) + py[k]) * P.cs2 + px[k]] = P.w * a;
                     a = 0.0;
                 }
                 acc[k] = a;
+                if (MODE == 3) {
+                    *reinterpret_cast<double2 *>(P.xo + gi) = va;
+                    *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = vb;
+                }
             } else {
-                int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
                 double2 oa2, ob2;
                 oa2.x = va.x + P.wod * (ba[k].x - ax0);
                 oa2.y = va.y + P.wod * (ba[k].y - ax1);
@@ -224,9 +289,11 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
         }
         __syncthreads();        // everyone is done with plane z-1's slot
         if (tid == 0) {
-            int p = z - 1 + ST_NS;
+            int p = z - 1 + NS;
             if (p <= z1) {
-                int k = (q - 1 + ST_NS) % ST_NS;      // == slot of plane z-1
+                int k = (q - 1 + NS) % NS;      // == slot of plane z-1
+                // generic-proxy reads/writes of this slot are ordered before the async-proxy refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(full + k, span_bytes);
                 bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
             }
@@ -236,75 +303,112 @@ __global__ void __launch_bounds__(ST_NT, 1) k_st3(const St3 P) {
 
 // ---------------------------------------------------------------- fix-ups for exception rows
 
-// xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly)
+// xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly).
+// 8 lanes per exception row: entries are loaded and gathered in parallel, fixed-order shuffle sum.
 template <int MODE>
 __global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ rows, int nexc, ExcOp E, RegR R,
                                                       int crow0, int frow0, int nglob,
                                                       const double *__restrict__ xi, const double *__restrict__ e,
                                                       const double *__restrict__ b, double *__restrict__ xo,
                                                       double omega) {
-    int s = blockIdx.x * OMG_TPB + threadIdx.x;
-    if (s >= nexc) return;
-    int i = rows[s];
-    int p0 = E.ptr[s], p1 = E.ptr[s + 1];
+    int gt = blockIdx.x * OMG_TPB + threadIdx.x;
+    int s = gt >> 3, k = gt & 7;
+    bool valid = s < nexc;
     double acc = 0.0;
-    for (int p = p0; p < p1; ++p) {
-        int j = E.col[p];
-        double v = xi[j];
-        if (MODE == 2) {
-            int jg = j + frow0;
-            if (jg >= 0 && jg < nglob) v += R.w * __ldg(e + reg_agg(R, jg) - crow0);
+    int i = 0;
+    if (valid) {
+        i = __ldg(rows + s);
+        int p0 = __ldg(E.ptr + s), p1 = __ldg(E.ptr + s + 1);
+        for (int p = p0 + k; p < p1; p += 8) {
+            int j = __ldg(E.col + p);
+            double v = xi[j];
+            if (MODE == 2) {
+                int jg = j + frow0;
+                if (jg >= 0 && jg < nglob) v += R.w * __ldg(e + reg_agg(R, jg) - crow0);
+            }
+            acc += __ldg(E.val + p) * v;
         }
-        acc += E.val[p] * v;
     }
-    double xc = xi[i];
-    if (MODE == 2) xc += R.w * __ldg(e + reg_agg(R, i + frow0) - crow0);
-    xo[i] = xc + omega * (b[i] - acc) / E.diag[s];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (valid && k == 0) {
+        double xc = xi[i];
+        if (MODE == 2) xc += R.w * __ldg(e + reg_agg(R, i + frow0) - crow0);
+        xo[i] = xc + omega * (b[i] - acc) / __ldg(E.diag + s);
+    }
 }
 
-// rc_I for coarse rows whose aggregate contains an exception row: the generic fused formula
+// rc_I for coarse rows whose aggregate contains an exception row: one warp per coarse row,
+// 4 lanes per fine row (entries of the exception CSR or the 7 band taps spread over the lanes),
+// fixed-order shuffle reductions.
 __global__ void __launch_bounds__(OMG_TPB) k_fix_crows(const int *__restrict__ crows, int ncrows, BandA<1> A, RegR R,
                                                        int crow0, int frow0, const double *__restrict__ x,
                                                        const double *__restrict__ b, double *__restrict__ rc) {
-    int t = blockIdx.x * OMG_TPB + threadIdx.x;
-    if (t >= ncrows) return;
-    int I = crows[t];
-    int cc = reg_cc(R, I + crow0) - frow0;
+    int gt = blockIdx.x * OMG_TPB + threadIdx.x;
+    int t = gt >> 5, lane = gt & 31;
+    int k = lane >> 2, sub = lane & 3;
+    bool valid = t < ncrows && k < R.k;
     double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < R.k) {
-            int i = cc + R.o[k];
-            double d;
-            double ax = A.ax(i, x, d);
-            acc += __ldg(b + i) - ax;
+    int I = 0, i = 0;
+    if (t < ncrows) I = __ldg(crows + t);
+    if (valid) {
+        i = reg_cc(R, I + crow0) - frow0 + R.o[k];
+        unsigned w = __ldg(A.e.mask + (i >> 5));
+        if ((w >> (i & 31)) & 1u) {
+            int s = __ldg(A.e.wpre + (i >> 5)) + __popc(w & ((1u << (i & 31)) - 1u));
+            int p0 = __ldg(A.e.ptr + s), p1 = __ldg(A.e.ptr + s + 1);
+            for (int p = p0 + sub; p < p1; p += 4) acc += __ldg(A.e.val + p) * x[__ldg(A.e.col + p)];
+        } else {
+            if (sub == 0) acc = A.b.diag * x[i];
+            for (int q = sub; q < A.b.nb; q += 4) acc += A.b.coef[q] * x[i + A.b.off[q]];
         }
     }
-    rc[I] = R.w * acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    double r = (valid && sub == 0) ? (__ldg(b + i) - acc) : 0.0;
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    if (t < ncrows && lane == 0) rc[I] = R.w * r;
 }
 
 // ---------------------------------------------------------------- host side
 
-// Does level L carry a 3-D 7-point constant band this path can run?
-static bool st3_params(Level &L, St3 *P) {
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// Does level L carry a 3-D 7-point constant band this path can run?  Fills geometry + tiling.
+static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     if (L.kind == OMG_KIND_CSR || L.band.nb != 6) return false;
     const BandOp &B = L.band;
     if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return false;
     if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;
     int S1 = B.off[4], S2 = B.off[5];
-    if (S1 < 64 || S1 > 2048 || (S1 & 1) || S2 % S1 != 0 || L.nloc % S2 != 0 || L.row0 % S2 != 0) return false;
+    if (S1 < 32 || S1 > 2048 || (S1 & 1) || S2 % S1 != 0 || L.nloc % S2 != 0 || L.row0 % S2 != 0) return false;
     int NY = S2 / S1, NZ = L.nloc / S2;
     if ((NY & 1) || (NZ & 1) || NZ < 2) return false;
     if (L.pad < S2 + S1) return false;
-    // rows per chunk: even, divides NY, TY*S1/4 patches <= ST_NT*ST_PPT
-    int maxTY = (4 * ST_NT * ST_PPT) / S1;
+    int NT = env_int("OMG_ST_NT", S1 >= 1024 ? 512 : 256);
+    if (NT != 256 && NT != 512 && NT != 128) NT = 256;
+    if (L.nloc <= (1 << 19)) NT = 128;        // small levels: more, smaller CTAs
+    // rows per chunk: even, divides NY, patches and transform pairs within the per-thread maxima
+    int maxTY = (4 * NT * ST_PPT) / S1;
+    int envTY = env_int("OMG_ST_TY", 0);
+    if (envTY > 0) maxTY = std::min(maxTY, envTY);
+    if (L.nloc <= (1 << 19)) maxTY = std::min(maxTY, 8);
     int TY = 0;
-    for (int t = std::min(maxTY, NY); t >= 2; --t)
-        if ((t % 2 == 0) && NY % t == 0) {
-            TY = t;
-            break;
-        }
+    for (int t = std::min(maxTY, NY); t >= 2; --t) {
+        if ((t & 1) || NY % t != 0) continue;
+        if (xf && (t + 2) * S1 > 2 * NT * ST_TPT) continue;
+        TY = t;
+        break;
+    }
     if (TY < 2) return false;
+    *NT_out = NT;
+    P->nloc = L.nloc;
     P->S1 = S1;
     P->S2 = S2;
     P->NZ = NZ;
@@ -321,33 +425,51 @@ static bool st3_params(Level &L, St3 *P) {
     P->c1 = B.coef[3];
     P->cS = B.coef[4];
     P->cP = B.coef[5];
-    // z-segments: even length, aim at >= 4 waves of CTAs
+    // ring depth: as deep as shared memory allows for the targeted CTAs per SM
+    size_t budget = (NT <= 256 ? 113 : 226) * 1024;
+    int NS = (int)std::min<size_t>(ST_MAXNS, (budget - 64) / ((size_t)P->SPAN * 8));
+    int envNS = env_int("OMG_ST_NS", 0);
+    if (envNS >= 4) NS = std::min(NS, envNS);
+    if (NS < 4) return false;
+    P->NS = NS;
+    // z-segments: even length, aim at ~4 waves of CTAs
     int chunks = NY / TY;
-    int target = std::max(1, (4 * std::max(g.sm_count, 1) + chunks - 1) / chunks);
+    int per_sm = NT <= 256 ? 2 : 1;
+    int target = std::max(1, (4 * per_sm * std::max(g.sm_count, 1) + chunks - 1) / chunks);
     int ZL = std::max(2, (NZ + target - 1) / target);
+    ZL = std::max(ZL, env_int("OMG_ST_ZL", 0));
     ZL += ZL & 1;
     ZL = std::min(ZL, NZ);
     P->ZL = ZL;
+    P->has_exc = 0;
     return true;
 }
 
-static size_t st3_smem(const St3 &P) { return (size_t)ST_NS * P.SPAN * sizeof(double) + ST_NS * sizeof(uint64_t); }
+static size_t st3_smem(const St3 &P) { return (size_t)P.NS * P.SPAN * sizeof(double) + ST_MAXNS * sizeof(uint64_t); }
 
-template <int MODE>
-static bool st3_launch(const St3 &P) {
+template <int MODE, int NT>
+static bool st3_launch_nt(const St3 &P) {
     static bool attr_set = false;
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_st3<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(k_st3<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         attr_set = true;
     }
     dim3 grid(P.NYg / P.TY, (P.NZ + P.ZL - 1) / P.ZL);
-    k_st3<MODE><<<grid, ST_NT, smem, g.stream>>>(P);
+    k_st3<MODE, NT><<<grid, NT, smem, g.stream>>>(P);
     return true;
+}
+
+template <int MODE>
+static bool st3_launch(const St3 &P, int NT) {
+    if (NT == 128) return st3_launch_nt<MODE, 128>(P);
+    if (NT == 256) return st3_launch_nt<MODE, 256>(P);
+    return st3_launch_nt<MODE, 512>(P);
 }
 
 static bool regular_matches(const Level &L, const St3 &P) {
@@ -357,34 +479,40 @@ static bool regular_matches(const Level &L, const St3 &P) {
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
     (void)h;
     St3 P{};
-    if (!st3_params(L, &P)) return false;
+    int NT;
+    if (!st3_params(L, &P, &NT, false)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     P.xi = xi;
     P.b = b;
     P.xo = xo;
     P.wod = omega / P.d;
-    if (!st3_launch<0>(P)) return false;
+    if (!st3_launch<0>(P, NT)) return false;
     if (L.kind == OMG_KIND_BAND_EXC)
-        k_fix_rows<0><<<cdiv(L.nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg, 0,
+        k_fix_rows<0><<<cdiv(L.nexc * 8, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg, 0,
                                                                        L.row0, L.n, xi, nullptr, b, xo, omega);
     return true;
+}
+
+static void fix_crows(Level &L, Level &C, const double *x, const double *b, double *rc) {
+    if (L.kind == OMG_KIND_BAND_EXC && L.nexc_crows > 0) {
+        BandA<1> A{L.band, L.exc_op()};
+        k_fix_crows<<<cdiv((int64_t)L.nexc_crows * 32, OMG_TPB), OMG_TPB, 0, g.stream>>>(
+            L.exc_crows, L.nexc_crows, A, L.reg, C.row0, L.row0, x, b, rc);
+    }
 }
 
 bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *x, const double *b, double *rc) {
     (void)h;
     St3 P{};
-    if (!st3_params(L, &P) || !regular_matches(L, P)) return false;
+    int NT;
+    if (!st3_params(L, &P, &NT, false) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
     P.xi = x;
     P.b = b;
-    P.xo = rc;
+    P.rc = rc;
     P.w = L.Rw;
-    if (!st3_launch<1>(P)) return false;
-    if (L.kind == OMG_KIND_BAND_EXC && L.nexc_crows > 0) {
-        BandA<1> A{L.band, L.exc_op()};
-        k_fix_crows<<<cdiv(L.nexc_crows, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_crows, L.nexc_crows, A, L.reg, C.row0,
-                                                                          L.row0, x, b, rc);
-    }
+    if (!st3_launch<1>(P, NT)) return false;
+    fix_crows(L, C, x, b, rc);
     return true;
 }
 
@@ -392,7 +520,8 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
                             const double *b, double *xo, double omega) {
     (void)h;
     St3 P{};
-    if (!st3_params(L, &P) || !regular_matches(L, P)) return false;
+    int NT;
+    if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     P.xi = xi;
     P.b = b;
@@ -400,9 +529,34 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
     P.e = e;
     P.w = L.Rw;
     P.wod = omega / P.d;
-    if (!st3_launch<2>(P)) return false;
+    if (!st3_launch<2>(P, NT)) return false;
     if (L.kind == OMG_KIND_BAND_EXC)
-        k_fix_rows<2><<<cdiv(L.nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg,
+        k_fix_rows<2><<<cdiv(L.nexc * 8, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg,
                                                                        C.row0, L.row0, L.n, xi, e, b, xo, omega);
+    return true;
+}
+
+// first Jacobi sweep from the zero iterate + residual + restriction, one pass over b
+bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
+                                       double *rc, double omega) {
+    (void)h;
+    St3 P{};
+    int NT;
+    if (g.nranks > 1) return false;      // needs b halos / neighbour exception flags across slabs
+    if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
+    if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
+    P.xi = b;
+    P.b = b;
+    P.xo = xo;
+    P.rc = rc;
+    P.w = L.Rw;
+    P.omega = omega;
+    P.wod = omega / P.d;
+    if (L.kind == OMG_KIND_BAND_EXC && !L.exc_diag_uniform) {
+        P.has_exc = 1;       // per-row a_ii lookups in the transform (slow path; not hit by Poisson hierarchies)
+        P.exc = L.exc_op();
+    }
+    if (!st3_launch<3>(P, NT)) return false;
+    fix_crows(L, C, xo, b, rc);
     return true;
 }

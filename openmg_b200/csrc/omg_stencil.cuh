@@ -11,3 +11,6 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
 // y = xi + R^T e ; xo = y + omega (b - A y)/diag      (prolong + correct + first post-smoothing sweep)
 bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
                             const double *b, double *xo, double omega);
+// xo = omega b/diag (first Jacobi sweep from the zero iterate) ; rc = R (b - A xo)
+bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
+                                       double *rc, double omega);
