@@ -78,6 +78,15 @@ int omg_device_info(char *buf, int buflen, int *sm_count, int64_t *mem_bytes);
 int omg_nccl_unique_id(unsigned char id[128]);
 int omg_dist_init(int rank, int nranks, const unsigned char id[128]);
 int omg_dist_rank(int *rank, int *nranks);
+/* Pure host logic: the row-slab partition of a hierarchy.  level_lead[l] = leading grid extent
+ * (problemShape[0] >> l), level_rows[l] = rows of A_l, level_regular[l] = level may be a slab
+ * (closed-form restriction, band operator).  Levels [0, *first_replicated) are slabs cut so that no
+ * restriction aggregate straddles two ranks; the others are replicated on every rank. */
+int omg_partition(int nlevels, const int64_t *level_lead, const int64_t *level_rows,
+                  const int32_t *level_regular, int nranks, int rank, int64_t agglomerate_below,
+                  int32_t *first_replicated, int64_t *row0, int64_t *nloc);
+/* rows [row0, row0+nloc) of level `level` live on this rank; slab = 0 for replicated levels */
+int omg_level_partition(const omg_hierarchy *h, int level, int64_t *row0, int64_t *nloc, int *slab);
 
 /* pinned host staging buffers for the host<->device legs of omg_solve */
 int omg_host_alloc(void **ptr, int64_t bytes);

@@ -33,6 +33,9 @@ SIGNATURES = {
     "omg_nccl_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "omg_dist_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
     "omg_dist_rank": (ctypes.c_int, [c_i32p, c_i32p]),
+    "omg_partition": (ctypes.c_int, [ctypes.c_int, c_i64p, c_i64p, c_i32p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int64, c_i32p, c_i64p, c_i64p]),
+    "omg_level_partition": (ctypes.c_int, [c_h, ctypes.c_int, c_i64p, c_i64p, c_i32p]),
     "omg_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]),
     "omg_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "omg_hierarchy_create_csr": (ctypes.c_int, [ctypes.POINTER(c_h), ctypes.c_int, c_i64p, ctypes.c_int,

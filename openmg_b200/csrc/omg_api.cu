@@ -27,15 +27,15 @@ int omg_set_error(int code, const char *fmt, ...) {
 int level0_from_csr(omg_hierarchy *h);
 int device_restriction_csr(int ndim, const int64_t *shape, int64_t *n_rows, int64_t *nnz, int **dptr, int **dcol,
                            double **dval);
-int launch_matvec(omg_hierarchy *h, Level &L, const double *x, double *y);
-int launch_residual(omg_hierarchy *h, Level &L, const double *x, const double *b, double *r);
-int launch_resnorm2(omg_hierarchy *h, Level &L, const double *x, const double *b, int slot);
+int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y);
+int launch_residual(omg_hierarchy *h, Level &L, double *x, const double *b, double *r);
+int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int slot);
 double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, int sweeps, double *cur,
                       const double *b);
-int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const double *b, double *rc);
+int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b, double *rc);
 int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const double *xi, double *xo);
 double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double *cur,
-                                      const double *e, const double *b);
+                                      double *e, const double *b, bool cur_halo_valid);
 int launch_coarse_solve(omg_hierarchy *h, const double *b, double *x);
 double *cycle_from_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double *cur);
 
@@ -73,6 +73,7 @@ int omg_init(int device) {
 
 void omg_finalize(void) {
     if (!g.inited) return;
+    dist_finalize();
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.stream2);
     g = Globals();
@@ -300,6 +301,15 @@ int omg_level_info(const omg_hierarchy *h, int level, int64_t *n, int64_t *nnzA,
     return OMG_OK;
 }
 
+int omg_level_partition(const omg_hierarchy *h, int level, int64_t *row0, int64_t *nloc, int *slab) {
+    CHECK_LEVEL(h, level);
+    const Level &L = h->lv[level];
+    if (row0) *row0 = L.row0;
+    if (nloc) *nloc = L.nloc;
+    if (slab) *slab = L.slab ? 1 : 0;
+    return OMG_OK;
+}
+
 int omg_level_band(const omg_hierarchy *h, int level, double *diag, int *nband, int64_t *offsets, double *coeffs) {
     CHECK_LEVEL(h, level);
     const Level &L = h->lv[level];
@@ -386,12 +396,15 @@ int omg_setup_times(const omg_hierarchy *h, double *upload_ms, double *galerkin_
 
 // ------------------------------------------------------------------ cycles
 
-static int up(double *dst, const double *src, int n) {
-    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, g.stream));
+// host vectors are GLOBAL (n entries); each rank moves the slice of the rows it owns
+static int up(const Level &L, double *dst_owned, const double *src_host) {
+    CUDA_TRY(cudaMemcpyAsync(dst_owned, src_host + L.row0, sizeof(double) * (size_t)L.nloc, cudaMemcpyHostToDevice,
+                             g.stream));
     return OMG_OK;
 }
-static int down(double *dst, const double *src, int n) {
-    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+static int down(const Level &L, double *dst_host, const double *src_owned) {
+    CUDA_TRY(cudaMemcpyAsync(dst_host + L.row0, src_owned, sizeof(double) * (size_t)L.nloc, cudaMemcpyDeviceToHost,
+                             g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     CUDA_TRY(cudaGetLastError());
     return OMG_OK;
@@ -513,8 +526,8 @@ int omg_cycle(omg_hierarchy *h, int level, const double *b_host, double *x_host,
         return download_x(h, x_host);
     }
     Level &L = h->lv[level];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    if (has_initial) OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    if (has_initial) OMG_TRY(up(L, L.xa, x_host));
     CycleCfg cfg{pre, post, smoother, 0, omega, 0};
     double *cur = cycle_from_level(h, level, cfg, has_initial ? L.xa : nullptr);
     if (level < h->nlev - 1) {
@@ -525,7 +538,7 @@ int omg_cycle(omg_hierarchy *h, int level, const double *b_host, double *x_host,
         nv = sqrt(h->norm2_host[1]);
     }
     if (norm) *norm = nv;
-    return down(x_host, cur, L.nloc);
+    return down(L, x_host, cur);
 }
 
 int omg_set_rhs(omg_hierarchy *h, const double *b_host) {
@@ -648,11 +661,11 @@ int omg_smooth(omg_hierarchy *h, int level, const double *b_host, double *x_host
     CHECK_LEVEL(h, level);
     OMG_TRY(check_cfg(sweeps, 0, smoother, omega));
     Level &L = h->lv[level];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
     double *cur = launch_smooth(h, L, smoother, omega, sweeps, L.xa, L.b);
     if (level == 0) h->cur0 = (cur == L.xb);
-    return down(x_host, cur, L.nloc);
+    return down(L, x_host, cur);
 }
 
 int omg_residual_restrict(omg_hierarchy *h, int level, const double *b_host, const double *x_host,
@@ -661,10 +674,10 @@ int omg_residual_restrict(omg_hierarchy *h, int level, const double *b_host, con
     if (level >= h->nlev - 1) return omg_set_error(OMG_EINVAL, "level %d has no restriction", level);
     Level &L = h->lv[level];
     Level &C = h->lv[level + 1];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
     OMG_TRY(launch_residual_restrict(h, level, L.xa, L.b, C.b));
-    return down(rc_host, C.b, C.nloc);
+    return down(C, rc_host, C.b);
 }
 
 int omg_prolong_correct(omg_hierarchy *h, int level, const double *ec_host, double *x_host) {
@@ -672,10 +685,10 @@ int omg_prolong_correct(omg_hierarchy *h, int level, const double *ec_host, doub
     if (level >= h->nlev - 1) return omg_set_error(OMG_EINVAL, "level %d has no restriction", level);
     Level &L = h->lv[level];
     Level &C = h->lv[level + 1];
-    OMG_TRY(up(C.xa, ec_host, C.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(C, C.xa, ec_host));
+    OMG_TRY(up(L, L.xa, x_host));
     OMG_TRY(launch_prolong_correct(h, level, C.xa, L.xa, L.xa));
-    return down(x_host, L.xa, L.nloc);
+    return down(L, x_host, L.xa);
 }
 
 int omg_prolong_correct_smooth(omg_hierarchy *h, int level, const double *b_host, const double *ec_host,
@@ -685,12 +698,12 @@ int omg_prolong_correct_smooth(omg_hierarchy *h, int level, const double *b_host
     OMG_TRY(check_cfg(sweeps, 0, smoother, omega));
     Level &L = h->lv[level];
     Level &C = h->lv[level + 1];
-    OMG_TRY(up(C.xa, ec_host, C.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    double *cur = launch_prolong_correct_smooth(h, level, smoother, omega, sweeps, L.xa, C.xa, L.b);
+    OMG_TRY(up(C, C.xa, ec_host));
+    OMG_TRY(up(L, L.xa, x_host));
+    OMG_TRY(up(L, L.b, b_host));
+    double *cur = launch_prolong_correct_smooth(h, level, smoother, omega, sweeps, L.xa, C.xa, L.b, false);
     if (level == 0) h->cur0 = (cur == L.xb);
-    return down(x_host, cur, L.nloc);
+    return down(L, x_host, cur);
 }
 
 int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, double *x_host, double threshold,
@@ -698,8 +711,8 @@ int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, d
     CHECK_LEVEL(h, level);
     OMG_TRY(check_cfg(0, 0, smoother, omega));
     Level &L = h->lv[level];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
     double *cur = L.xa;
     int it = 0;
     double nv = 0.0;
@@ -716,23 +729,23 @@ int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, d
     if (level == 0) h->cur0 = (cur == L.xb);
     if (sweeps_done) *sweeps_done = it;
     if (norm) *norm = nv;
-    return down(x_host, cur, L.nloc);
+    return down(L, x_host, cur);
 }
 
 int omg_coarse_solve(omg_hierarchy *h, const double *b_host, double *x_host) {
     CHECK_H(h);
     if (!h->Ainv) return omg_set_error(OMG_EINVAL, "this handle has no direct-solve factor");
     Level &L = h->lv[h->nlev - 1];
-    OMG_TRY(up(L.b, b_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
     OMG_TRY(launch_coarse_solve(h, L.b, L.xa));
-    return down(x_host, L.xa, L.nloc);
+    return down(L, x_host, L.xa);
 }
 
 int omg_residual_norm(omg_hierarchy *h, int level, const double *b_host, const double *x_host, double *norm) {
     CHECK_LEVEL(h, level);
     Level &L = h->lv[level];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
     if (level == 0) h->cur0 = 0;
     OMG_TRY(launch_resnorm2(h, L, L.xa, L.b, 1));
     CUDA_TRY(cudaMemcpyAsync(h->norm2_host + 1, h->norm2_dev + 1, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
@@ -744,38 +757,21 @@ int omg_residual_norm(omg_hierarchy *h, int level, const double *b_host, const d
 int omg_residual(omg_hierarchy *h, int level, const double *b_host, const double *x_host, double *r_host) {
     CHECK_LEVEL(h, level);
     Level &L = h->lv[level];
-    OMG_TRY(up(L.b, b_host, L.nloc));
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
     if (level == 0) h->cur0 = 0;
     OMG_TRY(launch_residual(h, L, L.xa, L.b, L.xb));
-    int rc = down(r_host, L.xb, L.nloc);
+    int rc = down(L, r_host, L.xb);
     return rc;
 }
 
 int omg_matvec(omg_hierarchy *h, int level, const double *x_host, double *y_host) {
     CHECK_LEVEL(h, level);
     Level &L = h->lv[level];
-    OMG_TRY(up(L.xa, x_host, L.nloc));
+    OMG_TRY(up(L, L.xa, x_host));
     if (level == 0) h->cur0 = 0;
     OMG_TRY(launch_matvec(h, L, L.xa, L.xb));
-    return down(y_host, L.xb, L.nloc);
-}
-
-// ------------------------------------------------------------------ distributed (single-rank defaults; omg_dist.cu overrides)
-
-int omg_nccl_unique_id(unsigned char id[128]) {
-    (void)id;
-    return omg_set_error(OMG_EUNSUPPORTED, "multi-GPU support not built yet");
-}
-int omg_dist_init(int rank, int nranks, const unsigned char id[128]) {
-    (void)id;
-    if (nranks == 1 && rank == 0) return OMG_OK;
-    return omg_set_error(OMG_EUNSUPPORTED, "multi-GPU support not built yet");
-}
-int omg_dist_rank(int *rank, int *nranks) {
-    if (rank) *rank = g.rank;
-    if (nranks) *nranks = g.nranks;
-    return OMG_OK;
+    return down(L, y_host, L.xb);
 }
 
 }   // extern "C"

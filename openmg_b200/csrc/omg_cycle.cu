@@ -9,6 +9,12 @@
 // coarsest: x = A_L^{-1} b (dense inverse applied as a GEMV)      :234
 // The per-level residual norm of :227 is only consumed at level 0 (:113,136); it is
 // computed there, on request.
+//
+// Indexing convention: level vectors are stored [pad | owned rows | pad]; `L.xa`, `L.xb`,
+// `L.b` point at the first OWNED row.  The generic kernels index by GLOBAL row, so they get
+// "virtual" pointers V(p) = p - row0 and the row range [row0, row0 + nloc); on one GPU
+// row0 == 0 and this is the identity.  Before an operator is applied to a vector of a slab
+// level its halos are filled from the neighbouring ranks (dist_halo_exchange).
 #include "omg_hier.cuh"
 #include "omg_kernels.cuh"
 #include "omg_stencil.cuh"
@@ -31,29 +37,38 @@
 
 static inline double *other(Level &L, double *cur) { return cur == L.xa ? L.xb : L.xa; }
 static inline int lvl(omg_hierarchy *h, const Level &L) { return (int)(&L - h->lv.data()); }
+template <class T>
+static inline T *V(const Level &L, T *p) { return p - L.row0; }
 
-int launch_matvec(omg_hierarchy *h, Level &L, const double *x, double *y) {
+int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y) {
+    dist_halo_exchange(h, L, x);
     ProfScope ps(h, "matvec", lvl(h, L), 16.0 * L.nloc);
-    DISPATCH_A(L, (k_matvec<decltype(A)><<<GRID(L.nloc)>>>(A, 0, L.nloc, x, y)));
+    int lo = L.row0, hi = L.row0 + L.nloc;
+    DISPATCH_A(L, (k_matvec<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, y))));
     h->launches++;
     return OMG_OK;
 }
 
-int launch_residual(omg_hierarchy *h, Level &L, const double *x, const double *b, double *r) {
+int launch_residual(omg_hierarchy *h, Level &L, double *x, const double *b, double *r) {
+    dist_halo_exchange(h, L, x);
     ProfScope ps(h, "residual", lvl(h, L), 24.0 * L.nloc);
-    DISPATCH_A(L, (k_residual<decltype(A)><<<GRID(L.nloc)>>>(A, 0, L.nloc, x, b, r)));
+    int lo = L.row0, hi = L.row0 + L.nloc;
+    DISPATCH_A(L, (k_residual<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, b), V(L, r))));
     h->launches++;
     return OMG_OK;
 }
 
-// sum of squares of b - A x into h->norm2_dev[slot]
-int launch_resnorm2(omg_hierarchy *h, Level &L, const double *x, const double *b, int slot) {
+// sum of squares of b - A x (all ranks) into h->norm2_dev[slot]
+int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int slot) {
+    dist_halo_exchange(h, L, x);
     int blocks = std::min(h->npartial, cdiv(L.nloc, OMG_TPB));
     blocks = std::max(blocks, 1);
     ProfScope ps(h, "residual_norm", lvl(h, L), 16.0 * L.nloc);
-    DISPATCH_A(L, (k_resnorm_partial<decltype(A)><<<blocks, OMG_TPB, 0, g.stream>>>(A, 0, L.nloc, x, b, h->partial)));
+    int lo = L.row0, hi = L.row0 + L.nloc;
+    DISPATCH_A(L, (k_resnorm_partial<decltype(A)><<<blocks, OMG_TPB, 0, g.stream>>>(A, lo, hi, V(L, x), V(L, b), h->partial)));
     k_final_sum<<<1, 1024, 0, g.stream>>>(h->partial, blocks, h->norm2_dev + slot);
     h->launches += 2;
+    if (L.slab) dist_allreduce_sum(h, h->norm2_dev + slot, 1);
     return OMG_OK;
 }
 
@@ -61,7 +76,7 @@ int launch_resnorm2(omg_hierarchy *h, Level &L, const double *x, const double *b
 // Returns the buffer holding the result.
 double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, int sweeps, double *cur,
                       const double *b) {
-    int n = L.nloc;
+    int n = L.nloc, lo = L.row0, hi = L.row0 + L.nloc;
     if (cur == nullptr && (sweeps == 0 || smoother != OMG_SMOOTH_JACOBI)) {
         cudaMemsetAsync(L.xa, 0, sizeof(double) * (size_t)n, g.stream);
         cur = L.xa;
@@ -70,14 +85,15 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
         for (int s = 0; s < sweeps; ++s) {
             if (cur == nullptr) {
                 ProfScope ps(h, "jacobi_zero", lvl(h, L), 16.0 * n);
-                DISPATCH_A(L, (k_jacobi_zero<decltype(A)><<<GRID(n)>>>(A, 0, n, b, L.xa, omega)));
+                DISPATCH_A(L, (k_jacobi_zero<decltype(A)><<<GRID(n)>>>(A, lo, hi, V(L, b), V(L, L.xa), omega)));
                 cur = L.xa;
             } else {
+                dist_halo_exchange(h, L, cur);
                 ProfScope ps(h, "jacobi", lvl(h, L), 24.0 * n);
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_jacobi(h, L, cur, b, out, omega)) {
                 } else {
-                    DISPATCH_A(L, (k_jacobi<decltype(A)><<<GRID(n)>>>(A, 0, n, cur, b, out, omega)));
+                    DISPATCH_A(L, (k_jacobi<decltype(A)><<<GRID(n)>>>(A, lo, hi, V(L, cur), V(L, b), V(L, out), omega)));
                 }
                 cur = out;
             }
@@ -86,13 +102,14 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
     } else if (smoother == OMG_SMOOTH_RBGS) {
         for (int s = 0; s < sweeps; ++s)
             for (int c = 0; c < 2; ++c) {
+                dist_halo_exchange(h, L, cur);
                 ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n);
                 double *out = other(L, cur);
-                DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, L.row0, 0, n, cur, b, out)));
+                DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
                 cur = out;
                 h->launches++;
             }
-    } else {   // lexicographic GS, in place
+    } else {   // lexicographic GS, in place (sequential: single GPU / replicated levels only)
         if (sweeps > 0) {
             ProfScope ps(h, "lexgs", lvl(h, L), 24.0 * n * sweeps);
             DISPATCH_A(L, (k_lexgs<decltype(A)><<<1, 32, 0, g.stream>>>(A, n, cur, b, sweeps)));
@@ -102,27 +119,27 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
     return cur;
 }
 
-// b_{l+1} = R_l (b_l - A_l x)
-int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const double *b, double *rc) {
+// b_{l+1} = R_l (b_l - A_l x); at the slab -> replicated transition the pieces are all-gathered
+int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b, double *rc) {
     Level &L = h->lv[l];
     Level &C = h->lv[l + 1];
+    dist_halo_exchange(h, L, x);
+    double *rcv = V(C, rc);                    // indexable by global coarse row
     if (L.regular) {
-        ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * C.nloc);
-        if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_residual_restrict(h, L, C, x, b, rc)) {
+        ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n);
+        if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_residual_restrict(h, L, C, x, b, rcv)) {
         } else {
-            DISPATCH_A(L, (k_residual_restrict<decltype(A)><<<GRID(C.nloc)>>>(A, L.reg, C.row0, L.row0, 0, C.nloc, x, b, rc)));
+            int clo = L.piece_row0, chi = L.piece_row0 + L.piece_n;
+            DISPATCH_A(L, (k_residual_restrict<decltype(A)><<<GRID(L.piece_n)>>>(A, L.reg, 0, 0, clo, chi, V(L, x), V(L, b), rcv)));
         }
         h->launches++;
     } else {
-        if (!L.r) {
-            if (h_alloc_t(h, &L.r_base, (size_t)L.nloc + 16, true) != OMG_OK) return OMG_ENOMEM;
-            L.r = L.r_base;
-        }
         launch_residual(h, L, x, b, L.r);
         ProfScope ps(h, "restrict", l, 8.0 * L.nloc + 8.0 * C.nloc);
         k_restrict_explicit<<<GRID(C.nloc)>>>(L.Rcc, L.reg, 0, C.nloc, L.r, rc);
         h->launches++;
     }
+    if (L.slab && !C.slab) return dist_allgather(h, rcv + L.piece_row0, rcv, (size_t)L.piece_n);
     return OMG_OK;
 }
 
@@ -130,9 +147,9 @@ int launch_residual_restrict(omg_hierarchy *h, int l, const double *x, const dou
 int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const double *xi, double *xo) {
     Level &L = h->lv[l];
     Level &C = h->lv[l + 1];
-    ProfScope ps(h, "prolong_correct", l, 16.0 * L.nloc + 8.0 * C.nloc);
+    ProfScope ps(h, "prolong_correct", l, 16.0 * L.nloc + 8.0 * L.piece_n);
     if (L.regular)
-        k_prolong_correct<<<GRID(L.nloc)>>>(L.reg, C.row0, L.row0, 0, L.nloc, e, xi, xo);
+        k_prolong_correct<<<GRID(L.nloc)>>>(L.reg, 0, 0, L.row0, L.row0 + L.nloc, V(C, e), V(L, xi), V(L, xo));
     else
         k_prolong_correct_csr<<<GRID(L.nloc)>>>(L.RTptr, L.RTcol, L.Rw, 0, L.nloc, e, xi, xo);
     h->launches++;
@@ -140,26 +157,22 @@ int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const doubl
 }
 
 // correction + post-smoothing (openmg/__init__.py:214-224).  Returns the result buffer.
+// cur_halo_valid: cur's halos were already filled (it was the input of the restriction).
 double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double *cur,
-                                      const double *e, const double *b) {
+                                      double *e, const double *b, bool cur_halo_valid) {
     Level &L = h->lv[l];
-    if (sweeps > 0 && smoother == OMG_SMOOTH_JACOBI && L.regular && !(h->flags & OMG_FLAG_NO_FUSED)) {
+    Level &C = h->lv[l + 1];
+    if (sweeps > 0 && smoother == OMG_SMOOTH_JACOBI && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_prolong_jacobi(h, L, C, nullptr, nullptr, nullptr, nullptr, omega)) {     // applicability probe
+        if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
+        dist_halo_exchange(h, C, e);
         double *out = other(L, cur);
-        bool ok;
         {
-            ProfScope ps(h, "prolong_jacobi", l, 24.0 * L.nloc + 8.0 * h->lv[l + 1].nloc);
-            ok = stencil_prolong_jacobi(h, L, h->lv[l + 1], cur, e, b, out, omega);
-            if (!ok && ps.idx >= 0) {   // not applicable: drop the record
-                cudaEventDestroy(h->prof.back().e0);
-                cudaEventDestroy(h->prof.back().e1);
-                h->prof.pop_back();
-                ps.idx = -1;
-            }
+            ProfScope ps(h, "prolong_jacobi", l, 24.0 * L.nloc + 8.0 * L.piece_n);
+            stencil_prolong_jacobi(h, L, C, cur, e, b, out, omega);
         }
-        if (ok) {
-            h->launches++;
-            return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
-        }
+        h->launches++;
+        return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
     }
     // in place: each thread reads and writes only its own x_j
     launch_prolong_correct(h, l, e, cur, cur);
@@ -183,7 +196,7 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
     }
     Level &C = h->lv[l + 1];
     bool fused0 = false;
-    if (cur == nullptr && cfg.pre == 1 && cfg.smoother == OMG_SMOOTH_JACOBI && L.regular &&
+    if (cur == nullptr && cfg.pre == 1 && cfg.smoother == OMG_SMOOTH_JACOBI && L.regular && !L.slab &&
         !(h->flags & OMG_FLAG_NO_FUSED)) {
         // zero initial iterate (openmg/__init__.py:191-192): sweep + residual + restriction in one pass over b
         ProfScope ps(h, "jacobi0_residual_restrict", l, 16.0 * L.nloc + 8.0 * C.nloc);
@@ -203,7 +216,8 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
         launch_residual_restrict(h, l, cur, L.b, C.b);
     }
     double *e = cycle_level(h, l + 1, cfg, nullptr);
-    return launch_prolong_correct_smooth(h, l, cfg.smoother, cfg.omega, cfg.post, cur, e, L.b);
+    // cur's halos were filled for the restriction (unfused path) and cur has not changed since
+    return launch_prolong_correct_smooth(h, l, cfg.smoother, cfg.omega, cfg.post, cur, e, L.b, !fused0);
 }
 
 double *cycle_from_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double *cur) {

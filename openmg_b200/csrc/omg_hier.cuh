@@ -22,7 +22,13 @@ struct Level {
     int n = 0;                 // global rows
     int row0 = 0;              // first owned global row (0 on one GPU)
     int nloc = 0;              // owned rows
-    int pad = 0;               // zero pad / halo width on each side (multiple of 16)
+    int pad = 0;               // zero pad / halo capacity on each side (multiple of 16)
+    bool slab = false;         // rows partitioned across ranks (else replicated / single GPU)
+    int halo = 0;              // elements exchanged with each neighbour before an operator application
+    int piece_row0 = 0;        // first coarse row this rank's fine slab restricts to
+    int piece_n = 0;           // number of coarse rows it produces
+    int exc_s0 = 0, exc_s1 = 0;     // exception slots whose row is owned
+    int crow_t0 = 0, crow_t1 = 0;   // entries of exc_crows whose coarse row this rank produces
     int ndim = 0;
     int shape[3] = {1, 1, 1};  // level shape, openmg/operators.py:131,136 (C order, as given)
     ColourRule colour{};
@@ -90,6 +96,7 @@ struct omg_hierarchy {
     bool profiling = false;          // per-kernel CUDA-event timing (omg_profile_cycle)
     std::vector<ProfRec> prof;
     int nlev = 0;
+    int first_replicated = 0;        // levels [0, first_replicated) are row slabs across ranks
     std::vector<Level> lv;
     std::vector<void *> allocs;      // everything cudaMalloc'ed for this hierarchy
     // coarse solve
@@ -125,6 +132,15 @@ int materialize_level_csr(omg_hierarchy *h, const Level &L, int **ptr, int **col
 
 // omg_cycle.cu
 int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);
+
+// omg_dist.cu
+int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v);
+int dist_allgather(omg_hierarchy *h, const double *piece, double *full, size_t count);
+int dist_allreduce_sum(omg_hierarchy *h, double *v, size_t count);
+void dist_finalize();
+extern "C" int omg_partition(int nlevels, const int64_t *level_lead, const int64_t *level_rows,
+                             const int32_t *level_regular, int nranks, int rank, int64_t agglomerate_below,
+                             int32_t *first_replicated, int64_t *row0, int64_t *nloc);
 
 // RAII event pair around one launch when h->profiling
 struct ProfScope {

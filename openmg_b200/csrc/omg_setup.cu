@@ -982,13 +982,102 @@ static int coarse_factor(omg_hierarchy *h) {
 
 // ------------------------------------------------------------------ vectors
 
+// first index t in sorted a[0..n) with a[t] >= v, for two values (device array)
+__global__ void k_lower_bounds(const int *__restrict__ a, int n, int v0, int v1, int *__restrict__ out) {
+    if (threadIdx.x > 1 || blockIdx.x) return;
+    int v = threadIdx.x ? v1 : v0;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[threadIdx.x] = lo;
+}
+
+static int lower_bounds(const int *a, int n, int v0, int v1, int *o0, int *o1) {
+    int *d = nullptr, hres[2] = {0, 0};
+    if (n > 0 && a) {
+        CUDA_TRY(cudaMalloc(&d, 2 * sizeof(int)));
+        k_lower_bounds<<<1, 2, 0, g.stream>>>(a, n, v0, v1, d);
+        CUDA_TRY(cudaMemcpyAsync(hres, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        cudaFree(d);
+    }
+    *o0 = hres[0];
+    *o1 = hres[1];
+    return OMG_OK;
+}
+
 static int alloc_vectors(omg_hierarchy *h) {
-    for (int l = 0; l < h->nlev; ++l) {
+    int nlev = h->nlev;
+    // ---- pads / halo widths from the band reach
+    std::vector<int> reach(nlev, 0), reach2(nlev, 0);
+    for (int l = 0; l < nlev; ++l) {
         Level &L = h->lv[l];
-        int reach = 0;
         if (L.kind != OMG_KIND_CSR)
-            for (int k = 0; k < L.band.nb; ++k) reach = std::max(reach, std::abs(L.band.off[k]));
-        L.pad = (2 * reach + 15) / 16 * 16;    // the 2.5-D stencil path stages plane -1 with its halo rows
+            for (int k = 0; k < L.band.nb; ++k) {
+                int a = std::abs(L.band.off[k]);
+                if (a > reach[l]) {
+                    reach2[l] = reach[l];
+                    reach[l] = a;
+                } else if (a > reach2[l] && a < reach[l])
+                    reach2[l] = a;
+            }
+        L.pad = (2 * reach[l] + 15) / 16 * 16;    // the 2.5-D stencil path stages plane -1 with its halo rows
+    }
+    // ---- slab partition (multi-GPU): row0 / nloc per level
+    std::vector<int64_t> lead(nlev), rows(nlev), row0(nlev), nloc(nlev);
+    std::vector<int32_t> regular(nlev);
+    for (int l = 0; l < nlev; ++l) {
+        Level &L = h->lv[l];
+        lead[l] = L.shape[0];
+        rows[l] = L.n;
+        // a slab level needs the closed-form restriction and a band operator (halo = band reach)
+        regular[l] = (L.hasR && L.regular && L.kind != OMG_KIND_CSR) ? 1 : 0;
+    }
+    const char *env = getenv("OMG_AGGLOMERATE_BELOW");
+    int64_t agg_below = env ? atoll(env) : (1ll << 19);
+    int32_t ld = 0;
+    for (;;) {
+        OMG_TRY(omg_partition(nlev, lead.data(), rows.data(), regular.data(), g.nranks, g.rank, agg_below, &ld,
+                              row0.data(), nloc.data()));
+        bool ok = true;
+        for (int l = 0; l < ld; ++l)
+            if (nloc[l] < 2 * (int64_t)h->lv[l].pad) {    // slab thinner than its halos: replicate from here on
+                regular[l] = 0;
+                ok = false;
+                break;
+            }
+        if (ok) break;
+    }
+    h->first_replicated = ld;
+    for (int l = 0; l < nlev; ++l) {
+        Level &L = h->lv[l];
+        L.slab = l < ld;
+        L.row0 = (int)row0[l];
+        L.nloc = (int)nloc[l];
+        L.halo = L.slab ? std::min(L.pad, (reach[l] + reach2[l] + 1) & ~1) : 0;
+        if (L.hasR) {
+            Level &C = h->lv[l + 1];
+            int k = L.Rk > 0 ? L.Rk : 1;
+            L.piece_row0 = L.slab ? (int)(row0[l] / k) : 0;
+            L.piece_n = L.slab ? (int)(nloc[l] / k) : C.n;
+        }
+        L.exc_s0 = 0;
+        L.exc_s1 = (int)L.nexc;
+        L.crow_t0 = 0;
+        L.crow_t1 = L.nexc_crows;
+        if (L.slab && L.kind == OMG_KIND_BAND_EXC) {
+            OMG_TRY(lower_bounds(L.exc_rows, (int)L.nexc, L.row0, L.row0 + L.nloc, &L.exc_s0, &L.exc_s1));
+            OMG_TRY(lower_bounds(L.exc_crows, L.nexc_crows, L.piece_row0, L.piece_row0 + L.piece_n, &L.crow_t0,
+                                 &L.crow_t1));
+        }
+    }
+    for (int l = 0; l < nlev; ++l) {
+        Level &L = h->lv[l];
         size_t len = (size_t)L.pad * 2 + (size_t)L.nloc + 16;
         OMG_TRY(h_alloc_t(h, &L.xa_base, len, true));
         OMG_TRY(h_alloc_t(h, &L.xb_base, len, true));

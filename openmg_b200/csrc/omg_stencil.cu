@@ -306,14 +306,15 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
 // xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly).
 // 8 lanes per exception row: entries are loaded and gathered in parallel, fixed-order shuffle sum.
 template <int MODE>
-__global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ rows, int nexc, ExcOp E, RegR R,
-                                                      int crow0, int frow0, int nglob,
-                                                      const double *__restrict__ xi, const double *__restrict__ e,
-                                                      const double *__restrict__ b, double *__restrict__ xo,
-                                                      double omega) {
+__global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ rows, int s0, int cnt, ExcOp E, RegR R,
+                                                      int nglob, const double *__restrict__ xi,
+                                                      const double *__restrict__ e, const double *__restrict__ b,
+                                                      double *__restrict__ xo, double omega) {
+    // all vector pointers are indexable by GLOBAL row / coarse row
+    const int crow0 = 0, frow0 = 0;
     int gt = blockIdx.x * OMG_TPB + threadIdx.x;
-    int s = gt >> 3, k = gt & 7;
-    bool valid = s < nexc;
+    int s = s0 + (gt >> 3), k = gt & 7;
+    bool valid = (gt >> 3) < cnt;
     double acc = 0.0;
     int i = 0;
     if (valid) {
@@ -343,8 +344,9 @@ __global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ ro
 // 4 lanes per fine row (entries of the exception CSR or the 7 band taps spread over the lanes),
 // fixed-order shuffle reductions.
 __global__ void __launch_bounds__(OMG_TPB) k_fix_crows(const int *__restrict__ crows, int ncrows, BandA<1> A, RegR R,
-                                                       int crow0, int frow0, const double *__restrict__ x,
-                                                       const double *__restrict__ b, double *__restrict__ rc) {
+                                                       const double *__restrict__ x, const double *__restrict__ b,
+                                                       double *__restrict__ rc) {
+    const int crow0 = 0, frow0 = 0;      // global-index pointers
     int gt = blockIdx.x * OMG_TPB + threadIdx.x;
     int t = gt >> 5, lane = gt & 31;
     int k = lane >> 2, sub = lane & 3;
@@ -476,6 +478,31 @@ static bool regular_matches(const Level &L, const St3 &P) {
     return L.regular && L.reg.alpha == 3 && L.reg.fs2 == P.S1 && L.reg.fs1 == P.NYg;
 }
 
+template <class T>
+static inline T *V(const Level &L, T *p) { return p - L.row0; }
+
+// fix-ups run on the owned exception slots / produced coarse rows only, with global-index pointers
+static void fix_rows(Level &L, Level *C, int mode, const double *xi, const double *e, const double *b, double *xo,
+                     double omega) {
+    int cnt = L.exc_s1 - L.exc_s0;
+    if (L.kind != OMG_KIND_BAND_EXC || cnt <= 0) return;
+    int grid = cdiv((int64_t)cnt * 8, OMG_TPB);
+    if (mode == 0)
+        k_fix_rows<0><<<grid, OMG_TPB, 0, g.stream>>>(L.exc_rows, L.exc_s0, cnt, L.exc_op(), L.reg, L.n, V(L, xi),
+                                                      nullptr, V(L, b), V(L, xo), omega);
+    else
+        k_fix_rows<2><<<grid, OMG_TPB, 0, g.stream>>>(L.exc_rows, L.exc_s0, cnt, L.exc_op(), L.reg, L.n, V(L, xi),
+                                                      V(*C, e), V(L, b), V(L, xo), omega);
+}
+
+static void fix_crows(Level &L, const double *x, const double *b, double *rcv) {
+    int cnt = L.crow_t1 - L.crow_t0;
+    if (L.kind != OMG_KIND_BAND_EXC || cnt <= 0) return;
+    BandA<1> A{L.band, L.exc_op()};
+    k_fix_crows<<<cdiv((int64_t)cnt * 32, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_crows + L.crow_t0, cnt, A, L.reg,
+                                                                          V(L, x), V(L, b), rcv);
+}
+
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
     (void)h;
     St3 P{};
@@ -487,35 +514,28 @@ bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *
     P.xo = xo;
     P.wod = omega / P.d;
     if (!st3_launch<0>(P, NT)) return false;
-    if (L.kind == OMG_KIND_BAND_EXC)
-        k_fix_rows<0><<<cdiv(L.nexc * 8, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg, 0,
-                                                                       L.row0, L.n, xi, nullptr, b, xo, omega);
+    fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
     return true;
 }
 
-static void fix_crows(Level &L, Level &C, const double *x, const double *b, double *rc) {
-    if (L.kind == OMG_KIND_BAND_EXC && L.nexc_crows > 0) {
-        BandA<1> A{L.band, L.exc_op()};
-        k_fix_crows<<<cdiv((int64_t)L.nexc_crows * 32, OMG_TPB), OMG_TPB, 0, g.stream>>>(
-            L.exc_crows, L.nexc_crows, A, L.reg, C.row0, L.row0, x, b, rc);
-    }
-}
-
-bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *x, const double *b, double *rc) {
+// rcv: coarse output indexable by GLOBAL coarse row
+bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *x, const double *b, double *rcv) {
     (void)h;
+    (void)C;
     St3 P{};
     int NT;
     if (!st3_params(L, &P, &NT, false) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
     P.xi = x;
     P.b = b;
-    P.rc = rc;
+    P.rc = rcv + L.piece_row0;
     P.w = L.Rw;
     if (!st3_launch<1>(P, NT)) return false;
-    fix_crows(L, C, x, b, rc);
+    fix_crows(L, x, b, rcv);
     return true;
 }
 
+// xi == nullptr: applicability probe only
 bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
                             const double *b, double *xo, double omega) {
     (void)h;
@@ -523,26 +543,27 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
     int NT;
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+    if (!xi) return true;
     P.xi = xi;
     P.b = b;
     P.xo = xo;
     P.e = e;
+    P.cz0 = C.row0 / (P.cs1 * P.cs2);
     P.w = L.Rw;
     P.wod = omega / P.d;
     if (!st3_launch<2>(P, NT)) return false;
-    if (L.kind == OMG_KIND_BAND_EXC)
-        k_fix_rows<2><<<cdiv(L.nexc * 8, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_rows, (int)L.nexc, L.exc_op(), L.reg,
-                                                                       C.row0, L.row0, L.n, xi, e, b, xo, omega);
+    fix_rows(L, &C, 2, xi, e, b, xo, omega);
     return true;
 }
 
-// first Jacobi sweep from the zero iterate + residual + restriction, one pass over b
+// first Jacobi sweep from the zero iterate + residual + restriction, one pass over b (single GPU /
+// replicated levels: across slabs it would need b halos and the neighbour's exception flags)
 bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
                                        double *rc, double omega) {
     (void)h;
     St3 P{};
     int NT;
-    if (g.nranks > 1) return false;      // needs b halos / neighbour exception flags across slabs
+    if (L.slab) return false;
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
     P.xi = b;
@@ -557,6 +578,6 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         P.exc = L.exc_op();
     }
     if (!st3_launch<3>(P, NT)) return false;
-    fix_crows(L, C, xo, b, rc);
+    fix_crows(L, xo, b, V(C, rc));
     return true;
 }

@@ -111,6 +111,13 @@ class _Handle(object):
         return {"n": n.value, "nnzA": nnzA.value, "nnzR": nnzR.value, "kind": _lib.KINDS[kind.value],
                 "nexc": nexc.value}
 
+    def local_range(self, level=0):
+        """(row0, nloc, is_slab): the rows of `level` this rank owns (everything on one GPU)."""
+        r0, nl = ctypes.c_int64(), ctypes.c_int64()
+        slab = ctypes.c_int32()
+        check(self._L.omg_level_partition(self._h, level, ctypes.byref(r0), ctypes.byref(nl), ctypes.byref(slab)))
+        return r0.value, nl.value, bool(slab.value)
+
     def level_band(self, level):
         diag = ctypes.c_double()
         nb = ctypes.c_int32()
@@ -252,7 +259,7 @@ class Hierarchy(_Handle):
         n = self.n(0)
         bb = _vec(b, n, "b")
         if out is None:
-            out = np.empty(n, np.float64)
+            out = np.zeros(n, np.float64)    # multi-GPU: only this rank's rows are filled (see openmg_b200.dist)
         has_initial = 0
         if x0 is not None:
             out[:] = _vec(x0, n, "x0")
