@@ -218,45 +218,62 @@ def reference_arm(args):
 
 # ---------------------------------------------------------------------------------- our arm
 
+WEAK_SHAPES = {   # per-GPU work fixed at 512^3 points; (a, b, a) shapes keep the reference's offsets consistent
+    1: ((512, 512, 512), 5),
+    2: ((512, 1024, 512), 6),
+    4: ((512, 2048, 512), 6),
+    8: ((1024, 1024, 1024), 6),      # BASELINE.json configs[4]
+}
+
+
 def ours(args):
     rank, world, barrier, allmax, dist = dist_setup(args.gpus)
     import openmg_b200 as omg
     from openmg_b200 import _lib
     from openmg_b200.hierarchy import Hierarchy
 
-    shape = tuple(args.shape)
-    s1 = len(shape) == 1
+    shape, gl = tuple(args.shape), args.grid_levels
+    scaling = "weak"
     if world > 1:
         from openmg_b200 import dist as omg_dist
         omg_dist.init_from_torch(dist)
+        if args.scaling == "weak" and shape == (512, 512, 512) and world in WEAK_SHAPES:
+            shape, gl = WEAK_SHAPES[world]
+        else:
+            scaling = "strong"
+    s1 = len(shape) == 1
     dev = _lib.device_info()
     A = problem(shape, s1)
     N = A.n
     t0 = time.perf_counter()
-    h = Hierarchy(A, shape, args.grid_levels - 1, 8)
+    h = Hierarchy(A, shape, gl - 1, 8)
     setup_wall = time.perf_counter() - t0
     nlev = h.nlevels
     sizes = [h.level_info(l)["n"] for l in range(nlev)]
     kinds = [h.level_info(l)["kind"] for l in range(nlev)]
+    row0, nloc, slab = h.local_range(0)
+    slabs = [h.local_range(l)[2] for l in range(nlev)]
 
-    # synthetic input: u uniform[0,1), b = A u; computed on the device from host u
-    u = np.random.RandomState(0).random_sample(N)
-    b_host = _lib.pinned_empty(N)
-    b_host[:] = h.matvec(u, 0)
-    x_host = _lib.pinned_empty(N)
-    h.set_rhs(b_host)
+    # synthetic input: u uniform[0,1), b = A u; b computed on the device from host u.
+    # One GPU: u = RandomState(0).random_sample(N).  N GPUs: each rank draws its own rows (seed = rank).
+    u = np.random.RandomState(rank if world > 1 else 0).random_sample(nloc)
+    b_host = _lib.pinned_empty(nloc)
+    b_host[:] = h.matvec_local(u, 0)
+    x_host = _lib.pinned_empty(nloc)
+    del u
+    h.set_rhs_local(b_host)
 
     # ---- device-resident timing: W warm-up cycles, then exactly K timed cycles
     h.bench_cycles(max(args.warmup, 3), args.pre, args.post, args.smoother, 0.8)
     barrier()
     with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as cs:
+        barrier()
         ms, launches = h.bench_cycles(args.steps, args.pre, args.post, args.smoother, 0.8)
         barrier()
-        # keep the sampler alive for at least a few samples on short runs
-        if ms < 600:
-            ms2, _ = h.bench_cycles(max(args.steps, int(600 / max(ms / args.steps, 1e-3))), args.pre, args.post,
-                                    args.smoother, 0.8)
-    ms = allmax(ms)
+        ms = allmax(ms)                     # identical on every rank from here on (collectives must match)
+        if ms < 600:   # keep the GPU under the same load a little longer so the sampler sees it
+            h.bench_cycles(max(args.steps, int(600 / max(ms / args.steps, 1e-3))), args.pre, args.post,
+                           args.smoother, 0.8)
     clocks = cs.summary()
     final_norm = h.current_norm()
     value = N * args.steps / (ms * 1e-3)
@@ -264,55 +281,61 @@ def ours(args):
     # ---- per-kernel shares (CUDA events, direct launches) and the roofline of the dominant kernel
     prof = h.profile_cycle(3, args.pre, args.post, args.smoother, 0.8)
     tot = sum(p["ms"] * p["launches"] / 3.0 for p in prof)
-    dom = max(prof, key=lambda p: p["ms"] * p["launches"])
+    dom = max(prof, key=lambda p: p["ms"] * p["launches"] if p["bytes"] > 0 else 0.0)
     peak, peak_src = peaks()
     ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
     Bcyc = algorithmic_bytes_per_cycle(sizes, args.pre, args.post)
     cyc_ach = Bcyc / (ms / args.steps * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "%s@L%d" % (dom["name"], dom["level"]), "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "share_of_cycle": dom["ms"] * dom["launches"] / 3.0 / tot if tot > 0 else None}
+                "share_of_cycle": dom["ms"] * dom["launches"] / 3.0 / tot if tot > 0 else None,
+                "algorithmic_bytes_per_launch": dom["bytes"]}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            roofline["traffic"] = json.load(open(tp)).get(dom["name"] + "@L%d" % dom["level"])
+            roofline["traffic"] = json.load(open(tp)).get("%s@L%d" % (dom["name"], dom["level"]))
         except Exception:  # noqa: BLE001
             pass
 
     # ---- end to end through the public call with HOST buffers (pinned), copies inside the timed region
     cyc_call = args.e2e_cycles
-    h.solve(b_host, None, args.pre, args.post, args.smoother, 0.8, 1, 0.0, out=x_host)       # warm
+    h.solve_local(b_host, x_host, args.pre, args.post, args.smoother, 0.8, 1, 0.0)       # warm
     barrier()
     ncalls = max(1, args.steps // cyc_call)
     t0 = time.perf_counter()
     for _ in range(ncalls):
-        x_host, done, norm, _h = h.solve(b_host, None, args.pre, args.post, args.smoother, 0.8, cyc_call, 0.0,
-                                         out=x_host)
+        done, norm = h.solve_local(b_host, x_host, args.pre, args.post, args.smoother, 0.8, cyc_call, 0.0)
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     e2e = {"value": N * cyc_call * ncalls / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": 8.0 * N / world / cyc_call, "d2h_bytes_per_step": 8.0 * N / world / cyc_call,
+           "h2d_bytes_per_step": 8.0 * N / cyc_call, "d2h_bytes_per_step": 8.0 * N / cyc_call,
            "cycles_per_call": cyc_call, "calls": ncalls, "ms_per_call": 1e3 * e2e_s / ncalls,
-           "call": "openmg_b200.Hierarchy.solve -> omg_solve (pinned host b in, host x out, final residual norm read)",
+           "call": "openmg_b200.Hierarchy.solve -> omg_solve (pinned host b in, host x out, final residual norm "
+                   "read; a step is one V-cycle, bytes are per cycle summed over ranks)",
            "final_norm": norm}
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
-    cpu = cpu_port_rate(shape, args.grid_levels, args.pre, args.post, args.smoother) if world == 1 else None
+    cpu = cpu_port_rate(shape if world == 1 else (512, 512, 512), gl, args.pre, args.post,
+                        args.smoother) if world == 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "vcycles_per_s": args.steps / (ms * 1e-3),
         "config": {"workload": "3-D Poisson %s fp64 (openmg generator), gridLevels=%d -> %d grids %s, V(%d,%d) %s, "
-                               "omega=0.8, b=A*u u~U[0,1) seed 0, zero initial iterate" % (
-                                   "x".join(map(str, shape)), args.grid_levels, nlev, sizes, args.pre, args.post,
-                                   args.smoother),
-                   "level_kinds": kinds, "l2_policy": "inputs larger than L2 (3 x %.2f GB level-0 vectors)" % (8e-9 * N),
+                               "omega=0.8, b=A*u u~U[0,1), zero initial iterate" % (
+                                   "x".join(map(str, shape)), gl, nlev, sizes, args.pre, args.post, args.smoother),
+                   "level_kinds": kinds, "level_is_slab": slabs,
+                   "l2_policy": "inputs larger than L2 (3 x %.2f GB level-0 vectors per GPU)" % (8e-9 * nloc),
                    "parallelism": "slab%d" % world, "device": dev["name"]},
         "roofline": roofline,
-        "cycle_roofline": {"algorithmic_bytes_per_cycle": Bcyc, "achieved": cyc_ach, "unit": "GB/s",
-                           "frac_of_measured_peak": cyc_ach / peak, "frac_of_8TBs_nominal": cyc_ach / 8000.0},
+        "cycle_roofline": {"algorithmic_bytes_per_cycle": Bcyc, "achieved_per_gpu": cyc_ach / world, "unit": "GB/s",
+                           "frac_of_measured_peak": cyc_ach / world / peak,
+                           "frac_of_8TBs_nominal": cyc_ach / world / 8000.0},
         "kernels": [{"kernel": "%s@L%d" % (p["name"], p["level"]), "launches_per_cycle": p["launches"] / 3.0,
                      "ms": p["ms"], "GBs": p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else None}
                     for p in prof],
@@ -334,6 +357,8 @@ def main():
     ap.add_argument("--pre", type=int, default=1)
     ap.add_argument("--post", type=int, default=1)
     ap.add_argument("--e2e-cycles", type=int, default=10)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = 512^3 points per GPU (default), strong = the same --shape on N GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -282,6 +282,32 @@ class Hierarchy(_Handle):
                                 SMOOTHERS[smoother], float(omega), ctypes.byref(norm)))
         return x, norm.value
 
+    # ---- multi-GPU: per-rank slices instead of global host vectors
+    def _virt(self, local_arr, level=0):
+        """Pointer p with p[row0 + i] == local_arr[i]: what the C-ABI (which takes GLOBAL host
+        vectors and touches only this rank's rows) needs when only the local slice exists."""
+        row0, nloc, _ = self.local_range(level)
+        a = local_arr
+        if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != nloc:
+            raise ValueError("local slice must be a contiguous float64 array of %d entries" % nloc)
+        return ctypes.cast(ctypes.c_void_p(a.ctypes.data - 8 * row0), _lib.c_f64p)
+
+    def matvec_local(self, x_loc, level=0):
+        y = np.empty_like(x_loc)
+        check(self._L.omg_matvec(self._h, level, self._virt(x_loc, level), self._virt(y, level)))
+        return y
+
+    def set_rhs_local(self, b_loc):
+        check(self._L.omg_set_rhs(self._h, self._virt(b_loc)))
+
+    def solve_local(self, b_loc, out_loc, pre=1, post=1, smoother="jacobi", omega=0.8, cycles=1, threshold=0.0):
+        """omg_solve on this rank's rows only (zero initial iterate). Returns (cycles_done, global norm)."""
+        done, norm = ctypes.c_int32(), ctypes.c_double()
+        check(self._L.omg_solve(self._h, self._virt(b_loc), self._virt(out_loc), 0, int(pre), int(post),
+                                SMOOTHERS[smoother], float(omega), int(cycles), float(threshold),
+                                ctypes.byref(done), ctypes.byref(norm), None, 0))
+        return done.value, norm.value
+
     # ---- device-resident benchmarking
     def set_rhs(self, b):
         bb = _vec(b, self.n(0), "b")
