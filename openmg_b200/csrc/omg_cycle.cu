@@ -105,7 +105,10 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 dist_halo_exchange(h, L, cur);
                 ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n);
                 double *out = other(L, cur);
-                DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
+                if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_colour_relax(h, L, c, cur, b, out)) {
+                } else {
+                    DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
+                }
                 cur = out;
                 h->launches++;
             }
@@ -173,6 +176,30 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
         }
         h->launches++;
         return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+    }
+    if (sweeps > 0 && smoother == OMG_SMOOTH_RBGS && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_prolong_colour_relax(h, L, C, 0, nullptr, nullptr, nullptr, nullptr)) {   // applicability probe
+        // correction fused with the colour-0 half of the first post-smoothing sweep
+        if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
+        dist_halo_exchange(h, C, e);
+        double *out = other(L, cur);
+        {
+            ProfScope ps(h, "prolong_rbgs_half", l, 12.0 * L.nloc + 8.0 * L.piece_n);
+            stencil_prolong_colour_relax(h, L, C, 0, cur, e, b, out);
+        }
+        h->launches++;
+        cur = out;
+        {   // colour-1 half of that sweep
+            dist_halo_exchange(h, L, cur);
+            ProfScope ps(h, "rbgs_half", l, 12.0 * L.nloc);
+            out = other(L, cur);
+            int lo = L.row0, hi = L.row0 + L.nloc;
+            if (!stencil_colour_relax(h, L, 1, cur, b, out))
+                DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(L.nloc)>>>(A, L.colour, 1, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
+            h->launches++;
+            cur = out;
+        }
+        return launch_smooth(h, L, smoother, omega, sweeps - 1, cur, b);
     }
     // in place: each thread reads and writes only its own x_j
     launch_prolong_correct(h, l, e, cur, cur);

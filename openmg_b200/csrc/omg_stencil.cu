@@ -45,6 +45,7 @@ struct St3 {
     int NYg;               // rows per plane
     int zg0, NZg;          // global index of local plane 0, global planes
     int cz0;               // global index of local coarse plane 0
+    int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
 
@@ -283,6 +284,17 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                 oa2.y = va.y + P.wod * (ba[k].y - ax1);
                 ob2.x = vb.x + P.wod * (bb[k].x - ax2);
                 ob2.y = vb.y + P.wod * (bb[k].y - ax3);
+                if (P.colour >= 0) {
+                    // two-colour half sweep: colour = (x + y + z) & 1; rows ya are even, x = 2px is even
+                    bool even_match = (((z + P.zg0) & 1) == P.colour);    // colour of (ya, 2px)
+                    if (even_match) {
+                        oa2.y = va.y;
+                        ob2.x = vb.x;
+                    } else {
+                        oa2.x = va.x;
+                        ob2.y = vb.y;
+                    }
+                }
                 *reinterpret_cast<double2 *>(P.xo + gi) = oa2;
                 *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = ob2;
             }
@@ -309,7 +321,8 @@ template <int MODE>
 __global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ rows, int s0, int cnt, ExcOp E, RegR R,
                                                       int nglob, const double *__restrict__ xi,
                                                       const double *__restrict__ e, const double *__restrict__ b,
-                                                      double *__restrict__ xo, double omega) {
+                                                      double *__restrict__ xo, double omega, ColourRule cr,
+                                                      int colour) {
     // all vector pointers are indexable by GLOBAL row / coarse row
     const int crow0 = 0, frow0 = 0;
     int gt = blockIdx.x * OMG_TPB + threadIdx.x;
@@ -319,6 +332,9 @@ __global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ ro
     int i = 0;
     if (valid) {
         i = __ldg(rows + s);
+        if (colour >= 0 && colour_of(cr, i) != colour) valid = false;   // other colour: the main kernel copied it
+    }
+    if (valid) {
         int p0 = __ldg(E.ptr + s), p1 = __ldg(E.ptr + s + 1);
         for (int p = p0 + k; p < p1; p += 8) {
             int j = __ldg(E.col + p);
@@ -444,6 +460,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     ZL = std::min(ZL, NZ);
     P->ZL = ZL;
     P->has_exc = 0;
+    P->colour = -1;
     return true;
 }
 
@@ -483,16 +500,16 @@ static inline T *V(const Level &L, T *p) { return p - L.row0; }
 
 // fix-ups run on the owned exception slots / produced coarse rows only, with global-index pointers
 static void fix_rows(Level &L, Level *C, int mode, const double *xi, const double *e, const double *b, double *xo,
-                     double omega) {
+                     double omega, int colour = -1) {
     int cnt = L.exc_s1 - L.exc_s0;
     if (L.kind != OMG_KIND_BAND_EXC || cnt <= 0) return;
     int grid = cdiv((int64_t)cnt * 8, OMG_TPB);
     if (mode == 0)
         k_fix_rows<0><<<grid, OMG_TPB, 0, g.stream>>>(L.exc_rows, L.exc_s0, cnt, L.exc_op(), L.reg, L.n, V(L, xi),
-                                                      nullptr, V(L, b), V(L, xo), omega);
+                                                      nullptr, V(L, b), V(L, xo), omega, L.colour, colour);
     else
         k_fix_rows<2><<<grid, OMG_TPB, 0, g.stream>>>(L.exc_rows, L.exc_s0, cnt, L.exc_op(), L.reg, L.n, V(L, xi),
-                                                      V(*C, e), V(L, b), V(L, xo), omega);
+                                                      V(*C, e), V(L, b), V(L, xo), omega, L.colour, colour);
 }
 
 static void fix_crows(Level &L, const double *x, const double *b, double *rcv) {
@@ -579,5 +596,48 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
     }
     if (!st3_launch<3>(P, NT)) return false;
     fix_crows(L, xo, b, V(C, rc));
+    return true;
+}
+
+static bool grid_colour_matches(const Level &L, const St3 &P) {
+    return !L.colour.flat && L.colour.alpha == 3 && L.colour.s2 == P.S1 && L.colour.s1 == P.NYg;
+}
+
+// one colour half-sweep of the two-colour Gauss-Seidel: xo = xi, rows of `colour` relaxed with omega = 1
+bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *xi, const double *b, double *xo) {
+    (void)h;
+    St3 P{};
+    int NT;
+    if (!st3_params(L, &P, &NT, false) || !grid_colour_matches(L, P)) return false;
+    if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+    P.xi = xi;
+    P.b = b;
+    P.xo = xo;
+    P.wod = 1.0 / P.d;
+    P.colour = colour;
+    if (!st3_launch<0>(P, NT)) return false;
+    fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
+    return true;
+}
+
+// y = xi + R^T e ; xo = y with the rows of `colour` relaxed (first half of the post-smoothing sweep)
+bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colour, const double *xi,
+                                  const double *e, const double *b, double *xo) {
+    (void)h;
+    St3 P{};
+    int NT;
+    if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P) || !grid_colour_matches(L, P)) return false;
+    if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+    if (!xi) return true;
+    P.xi = xi;
+    P.b = b;
+    P.xo = xo;
+    P.e = e;
+    P.cz0 = C.row0 / (P.cs1 * P.cs2);
+    P.w = L.Rw;
+    P.wod = 1.0 / P.d;
+    P.colour = colour;
+    if (!st3_launch<2>(P, NT)) return false;
+    fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
     return true;
 }

@@ -14,3 +14,7 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
 // xo = omega b/diag (first Jacobi sweep from the zero iterate) ; rc = R (b - A xo)
 bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
                                        double *rc, double omega);
+// two-colour Gauss-Seidel half sweeps (grid-parity colouring of 3-D levels)
+bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *xi, const double *b, double *xo);
+bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colour, const double *xi,
+                                  const double *e, const double *b, double *xo);
