@@ -66,7 +66,11 @@ int omg_init(int device) {
     g.device = device;
     g.sm_count = p.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+    {
+        int lo_pri = 0, hi_pri = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CUDA_TRY(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, hi_pri));   // comm stream
+    }
     g.inited = true;
     return OMG_OK;
 }

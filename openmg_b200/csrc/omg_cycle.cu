@@ -42,6 +42,7 @@ static inline T *V(const Level &L, T *p) { return p - L.row0; }
 
 int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y) {
     dist_halo_exchange(h, L, x);
+    dist_halo_wait(h);
     ProfScope ps(h, "matvec", lvl(h, L), 16.0 * L.nloc);
     int lo = L.row0, hi = L.row0 + L.nloc;
     DISPATCH_A(L, (k_matvec<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, y))));
@@ -51,6 +52,7 @@ int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y) {
 
 int launch_residual(omg_hierarchy *h, Level &L, double *x, const double *b, double *r) {
     dist_halo_exchange(h, L, x);
+    dist_halo_wait(h);
     ProfScope ps(h, "residual", lvl(h, L), 24.0 * L.nloc);
     int lo = L.row0, hi = L.row0 + L.nloc;
     DISPATCH_A(L, (k_residual<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, b), V(L, r))));
@@ -61,6 +63,7 @@ int launch_residual(omg_hierarchy *h, Level &L, double *x, const double *b, doub
 // sum of squares of b - A x (all ranks) into h->norm2_dev[slot]
 int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int slot) {
     dist_halo_exchange(h, L, x);
+    dist_halo_wait(h);
     int blocks = std::min(h->npartial, cdiv(L.nloc, OMG_TPB));
     blocks = std::max(blocks, 1);
     ProfScope ps(h, "residual_norm", lvl(h, L), 16.0 * L.nloc);
@@ -93,6 +96,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_jacobi(h, L, cur, b, out, omega)) {
                 } else {
+                    dist_halo_wait(h);
                     DISPATCH_A(L, (k_jacobi<decltype(A)><<<GRID(n)>>>(A, lo, hi, V(L, cur), V(L, b), V(L, out), omega)));
                 }
                 cur = out;
@@ -107,12 +111,14 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_colour_relax(h, L, c, cur, b, out)) {
                 } else {
+                    dist_halo_wait(h);
                     DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(n)>>>(A, L.colour, c, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
                 }
                 cur = out;
                 h->launches++;
             }
     } else {   // lexicographic GS, in place (sequential: single GPU / replicated levels only)
+        dist_halo_wait(h);
         if (sweeps > 0) {
             ProfScope ps(h, "lexgs", lvl(h, L), 24.0 * n * sweeps);
             DISPATCH_A(L, (k_lexgs<decltype(A)><<<1, 32, 0, g.stream>>>(A, n, cur, b, sweeps)));
@@ -132,6 +138,7 @@ int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b
         ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n);
         if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_residual_restrict(h, L, C, x, b, rcv)) {
         } else {
+            dist_halo_wait(h);
             int clo = L.piece_row0, chi = L.piece_row0 + L.piece_n;
             DISPATCH_A(L, (k_residual_restrict<decltype(A)><<<GRID(L.piece_n)>>>(A, L.reg, 0, 0, clo, chi, V(L, x), V(L, b), rcv)));
         }
@@ -194,8 +201,10 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
             ProfScope ps(h, "rbgs_half", l, 12.0 * L.nloc);
             out = other(L, cur);
             int lo = L.row0, hi = L.row0 + L.nloc;
-            if (!stencil_colour_relax(h, L, 1, cur, b, out))
+            if (!stencil_colour_relax(h, L, 1, cur, b, out)) {
+                dist_halo_wait(h);
                 DISPATCH_A(L, (k_colour_relax<decltype(A)><<<GRID(L.nloc)>>>(A, L.colour, 1, 0, lo, hi, V(L, cur), V(L, b), V(L, out))));
+            }
             h->launches++;
             cur = out;
         }
@@ -258,6 +267,7 @@ int run_cycle(omg_hierarchy *h, const CycleCfg &cfg) {
     cur = cycle_level(h, 0, cfg, cur);
     h->cur0 = (cur == L0.xb) ? 1 : 0;
     if (cfg.with_norm) launch_resnorm2(h, L0, cur, L0.b, 0);
+    dist_halo_wait(h);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "cycle launch failed: %s", cudaGetErrorString(e));
     return OMG_OK;

@@ -137,38 +137,76 @@ int omg_partition(int nlevels, const int64_t *level_lead, const int64_t *level_r
 
 // ---------------------------------------------------------------- device-side collectives (library stream)
 
-// Fill the halos of vector v (owned pointer) of slab level L: hw elements from each neighbour.
+// All NCCL traffic runs on the library's second (high-priority) stream so that a halo exchange can
+// overlap the interior planes of the kernel that consumes it:
+//   compute stream:  ... producer | interior z-segments ........ | wait(join) | boundary z-segments
+//   comm stream:         wait(fork) | ncclSend/ncclRecv | record(join)
+static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
+static int comm_fork() {
+    if (!ev_fork) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ev_fork, g.stream));
+    CUDA_TRY(cudaStreamWaitEvent(g.stream2, ev_fork, 0));
+    return OMG_OK;
+}
+
+// Start filling the halos of vector v (owned pointer) of slab level L: hw elements from each
+// neighbour.  Asynchronous: dist_halo_wait() makes the compute stream wait for it.
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v) {
     if (g.nranks == 1 || !L.slab) return OMG_OK;
-    ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0);
+    OMG_TRY(comm_fork());
+    ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0, g.stream2);
     ncclComm_t comm = (ncclComm_t)g.nccl_comm;
     size_t hw = (size_t)L.halo;
     NCCL_TRY(nccl.GroupStart());
     if (g.rank > 0) {
-        NCCL_TRY(nccl.Send(v, hw, ncclFloat64, g.rank - 1, comm, g.stream));                  // my bottom rows -> lower
-        NCCL_TRY(nccl.Recv(v - hw, hw, ncclFloat64, g.rank - 1, comm, g.stream));             // lower's top rows
+        NCCL_TRY(nccl.Send(v, hw, ncclFloat64, g.rank - 1, comm, g.stream2));                  // my bottom rows -> lower
+        NCCL_TRY(nccl.Recv(v - hw, hw, ncclFloat64, g.rank - 1, comm, g.stream2));             // lower's top rows
     }
     if (g.rank < g.nranks - 1) {
-        NCCL_TRY(nccl.Send(v + L.nloc - hw, hw, ncclFloat64, g.rank + 1, comm, g.stream));    // my top rows -> upper
-        NCCL_TRY(nccl.Recv(v + L.nloc, hw, ncclFloat64, g.rank + 1, comm, g.stream));         // upper's bottom rows
+        NCCL_TRY(nccl.Send(v + L.nloc - hw, hw, ncclFloat64, g.rank + 1, comm, g.stream2));    // my top rows -> upper
+        NCCL_TRY(nccl.Recv(v + L.nloc, hw, ncclFloat64, g.rank + 1, comm, g.stream2));         // upper's bottom rows
     }
     NCCL_TRY(nccl.GroupEnd());
+    CUDA_TRY(cudaEventRecord(ev_join, g.stream2));
+    h->halo_pending = true;
     h->launches++;
+    return OMG_OK;
+}
+
+// the compute stream waits for every exchange started so far
+int dist_halo_wait(omg_hierarchy *h) {
+    if (!h->halo_pending) return OMG_OK;
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, ev_join, 0));
+    h->halo_pending = false;
     return OMG_OK;
 }
 
 // full[0..n) on every rank from the equal-sized pieces (piece of rank r at full + r*count)
 int dist_allgather(omg_hierarchy *h, const double *piece, double *full, size_t count) {
     if (g.nranks == 1) return OMG_OK;
-    ProfScope ps(h, "allgather", -1, 0.0);
-    NCCL_TRY(nccl.AllGather(piece, full, count, ncclFloat64, (ncclComm_t)g.nccl_comm, g.stream));
+    OMG_TRY(dist_halo_wait(h));
+    OMG_TRY(comm_fork());
+    {
+        ProfScope ps(h, "allgather", -1, 0.0, g.stream2);
+        NCCL_TRY(nccl.AllGather(piece, full, count, ncclFloat64, (ncclComm_t)g.nccl_comm, g.stream2));
+    }
+    CUDA_TRY(cudaEventRecord(ev_join, g.stream2));
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, ev_join, 0));
     h->launches++;
     return OMG_OK;
 }
 
 int dist_allreduce_sum(omg_hierarchy *h, double *v, size_t count) {
     if (g.nranks == 1) return OMG_OK;
-    NCCL_TRY(nccl.AllReduce(v, v, count, ncclFloat64, ncclSum, (ncclComm_t)g.nccl_comm, g.stream));
+    OMG_TRY(dist_halo_wait(h));
+    OMG_TRY(comm_fork());
+    NCCL_TRY(nccl.AllReduce(v, v, count, ncclFloat64, ncclSum, (ncclComm_t)g.nccl_comm, g.stream2));
+    CUDA_TRY(cudaEventRecord(ev_join, g.stream2));
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, ev_join, 0));
     h->launches++;
     return OMG_OK;
 }

@@ -94,6 +94,7 @@ struct ProfRec {
 struct omg_hierarchy {
     int flags = 0;
     bool profiling = false;          // per-kernel CUDA-event timing (omg_profile_cycle)
+    bool halo_pending = false;       // a halo exchange is in flight on the comm stream
     std::vector<ProfRec> prof;
     int nlev = 0;
     int first_replicated = 0;        // levels [0, first_replicated) are row slabs across ranks
@@ -135,6 +136,7 @@ int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);
 
 // omg_dist.cu
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v);
+int dist_halo_wait(omg_hierarchy *h);
 int dist_allgather(omg_hierarchy *h, const double *piece, double *full, size_t count);
 int dist_allreduce_sum(omg_hierarchy *h, double *v, size_t count);
 void dist_finalize();
@@ -146,16 +148,18 @@ extern "C" int omg_partition(int nlevels, const int64_t *level_lead, const int64
 struct ProfScope {
     omg_hierarchy *h;
     int idx;
-    ProfScope(omg_hierarchy *h_, const char *name, int level, double bytes) : h(h_), idx(-1) {
+    cudaStream_t st;
+    ProfScope(omg_hierarchy *h_, const char *name, int level, double bytes, cudaStream_t stream = nullptr)
+        : h(h_), idx(-1), st(stream ? stream : g.stream) {
         if (!h->profiling) return;
         ProfRec r{name, level, bytes, nullptr, nullptr};
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
-        cudaEventRecord(r.e0, g.stream);
+        cudaEventRecord(r.e0, st);
         h->prof.push_back(r);
         idx = (int)h->prof.size() - 1;
     }
     ~ProfScope() {
-        if (idx >= 0) cudaEventRecord(h->prof[idx].e1, g.stream);
+        if (idx >= 0) cudaEventRecord(h->prof[idx].e1, st);
     }
 };

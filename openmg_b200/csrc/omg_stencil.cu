@@ -46,6 +46,7 @@ struct St3 {
     int zg0, NZg;          // global index of local plane 0, global planes
     int cz0;               // global index of local coarse plane 0
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
+    int seg_base, nseg, boundary;   // z-segment of a CTA: blockIdx.y + seg_base, or {0, nseg-1} when `boundary`
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
 
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     constexpr bool XF = (MODE == 2 || MODE == 3);
     const int NS = P.NS;
     const int tid = threadIdx.x;
-    const int z0 = blockIdx.y * P.ZL;
+    const int seg = P.boundary ? (blockIdx.y == 0 ? 0 : P.nseg - 1) : (int)blockIdx.y + P.seg_base;
+    const int z0 = seg * P.ZL;
     const int z1 = min(z0 + P.ZL, P.NZ);
     const int y0 = blockIdx.x * P.TY;
     const long long span0 = (long long)y0 * P.S1 - P.S1;      // in-plane start of the span (row y0-1)
@@ -467,7 +469,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
 static size_t st3_smem(const St3 &P) { return (size_t)P.NS * P.SPAN * sizeof(double) + ST_MAXNS * sizeof(uint64_t); }
 
 template <int MODE, int NT>
-static bool st3_launch_nt(const St3 &P) {
+static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     static bool attr_set = false;
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
@@ -479,16 +481,31 @@ static bool st3_launch_nt(const St3 &P) {
         }
         attr_set = true;
     }
-    dim3 grid(P.NYg / P.TY, (P.NZ + P.ZL - 1) / P.ZL);
-    k_st3<MODE, NT><<<grid, NT, smem, g.stream>>>(P);
+    const int chunks = P.NYg / P.TY;
+    P.nseg = (P.NZ + P.ZL - 1) / P.ZL;
+    if (h->halo_pending && P.nseg >= 3) {
+        // interior z-segments do not touch the halo planes: run them while the exchange is in flight
+        P.boundary = 0;
+        P.seg_base = 1;
+        k_st3<MODE, NT><<<dim3(chunks, P.nseg - 2), NT, smem, g.stream>>>(P);
+        dist_halo_wait(h);
+        P.boundary = 1;
+        k_st3<MODE, NT><<<dim3(chunks, 2), NT, smem, g.stream>>>(P);
+        h->launches++;
+    } else {
+        dist_halo_wait(h);
+        P.boundary = 0;
+        P.seg_base = 0;
+        k_st3<MODE, NT><<<dim3(chunks, P.nseg), NT, smem, g.stream>>>(P);
+    }
     return true;
 }
 
 template <int MODE>
-static bool st3_launch(const St3 &P, int NT) {
-    if (NT == 128) return st3_launch_nt<MODE, 128>(P);
-    if (NT == 256) return st3_launch_nt<MODE, 256>(P);
-    return st3_launch_nt<MODE, 512>(P);
+static bool st3_launch(omg_hierarchy *h, const St3 &P, int NT) {
+    if (NT == 128) return st3_launch_nt<MODE, 128>(h, P);
+    if (NT == 256) return st3_launch_nt<MODE, 256>(h, P);
+    return st3_launch_nt<MODE, 512>(h, P);
 }
 
 static bool regular_matches(const Level &L, const St3 &P) {
@@ -521,7 +538,6 @@ static void fix_crows(Level &L, const double *x, const double *b, double *rcv) {
 }
 
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
-    (void)h;
     St3 P{};
     int NT;
     if (!st3_params(L, &P, &NT, false)) return false;
@@ -530,14 +546,13 @@ bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *
     P.b = b;
     P.xo = xo;
     P.wod = omega / P.d;
-    if (!st3_launch<0>(P, NT)) return false;
+    if (!st3_launch<0>(h, P, NT)) return false;
     fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
     return true;
 }
 
 // rcv: coarse output indexable by GLOBAL coarse row
 bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *x, const double *b, double *rcv) {
-    (void)h;
     (void)C;
     St3 P{};
     int NT;
@@ -547,7 +562,7 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
     P.b = b;
     P.rc = rcv + L.piece_row0;
     P.w = L.Rw;
-    if (!st3_launch<1>(P, NT)) return false;
+    if (!st3_launch<1>(h, P, NT)) return false;
     fix_crows(L, x, b, rcv);
     return true;
 }
@@ -555,7 +570,6 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
 // xi == nullptr: applicability probe only
 bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
                             const double *b, double *xo, double omega) {
-    (void)h;
     St3 P{};
     int NT;
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
@@ -568,7 +582,7 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
     P.cz0 = C.row0 / (P.cs1 * P.cs2);
     P.w = L.Rw;
     P.wod = omega / P.d;
-    if (!st3_launch<2>(P, NT)) return false;
+    if (!st3_launch<2>(h, P, NT)) return false;
     fix_rows(L, &C, 2, xi, e, b, xo, omega);
     return true;
 }
@@ -577,7 +591,6 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
 // replicated levels: across slabs it would need b halos and the neighbour's exception flags)
 bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
                                        double *rc, double omega) {
-    (void)h;
     St3 P{};
     int NT;
     if (L.slab) return false;
@@ -594,7 +607,7 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         P.has_exc = 1;       // per-row a_ii lookups in the transform (slow path; not hit by Poisson hierarchies)
         P.exc = L.exc_op();
     }
-    if (!st3_launch<3>(P, NT)) return false;
+    if (!st3_launch<3>(h, P, NT)) return false;
     fix_crows(L, xo, b, V(C, rc));
     return true;
 }
@@ -605,7 +618,6 @@ static bool grid_colour_matches(const Level &L, const St3 &P) {
 
 // one colour half-sweep of the two-colour Gauss-Seidel: xo = xi, rows of `colour` relaxed with omega = 1
 bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *xi, const double *b, double *xo) {
-    (void)h;
     St3 P{};
     int NT;
     if (!st3_params(L, &P, &NT, false) || !grid_colour_matches(L, P)) return false;
@@ -615,7 +627,7 @@ bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *
     P.xo = xo;
     P.wod = 1.0 / P.d;
     P.colour = colour;
-    if (!st3_launch<0>(P, NT)) return false;
+    if (!st3_launch<0>(h, P, NT)) return false;
     fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
     return true;
 }
@@ -623,7 +635,6 @@ bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *
 // y = xi + R^T e ; xo = y with the rows of `colour` relaxed (first half of the post-smoothing sweep)
 bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colour, const double *xi,
                                   const double *e, const double *b, double *xo) {
-    (void)h;
     St3 P{};
     int NT;
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P) || !grid_colour_matches(L, P)) return false;
@@ -637,7 +648,7 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
     P.w = L.Rw;
     P.wod = 1.0 / P.d;
     P.colour = colour;
-    if (!st3_launch<2>(P, NT)) return false;
+    if (!st3_launch<2>(h, P, NT)) return false;
     fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
     return true;
 }
