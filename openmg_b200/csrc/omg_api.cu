@@ -108,6 +108,8 @@ int omg_host_free(void *ptr) {
 void omg_hierarchy_destroy(omg_hierarchy *h) {
     if (!h) return;
     if (g.inited) cudaStreamSynchronize(g.stream);
+    if (g.inited) cudaStreamSynchronize(g.stream2);
+    dist_peer_teardown(h);
     for (auto &kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void *p : h->allocs) cudaFree(p);

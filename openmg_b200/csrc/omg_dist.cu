@@ -153,11 +153,152 @@ static int comm_fork() {
     return OMG_OK;
 }
 
+// ---- peer-memory path: copy-engine pulls ordered by device-side flags (no SMs, no NCCL kernels)
+//
+//   signal_ready: "my boundary rows of this buffer are final"   -> epoch written into both neighbours' flags
+//   wait_ready  : spin until both neighbours said so
+//   2 x cudaMemcpyAsync (peer -> my halos), copy engines over NVLink
+//   signal_done : "I have pulled"                                 -> neighbours may overwrite their rows again
+//   wait_done   : spin until both neighbours have pulled from me
+// Epochs live in device memory, so a captured CUDA graph can be replayed.
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_halo_signal(unsigned long long *epoch, int bump, unsigned long long *f_dn, unsigned long long *f_up) {
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long e = *epoch + (unsigned long long)bump;
+    *epoch = e;
+    __threadfence_system();
+    if (f_dn) st_release_sys(f_dn, e);
+    if (f_up) st_release_sys(f_up, e);
+}
+
+__global__ void k_halo_spin(const unsigned long long *epoch, const unsigned long long *f_dn,
+                            const unsigned long long *f_up) {
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long e = *epoch;
+    if (f_dn)
+        while (ld_acquire_sys(f_dn) < e) __nanosleep(64);
+    if (f_up)
+        while (ld_acquire_sys(f_up) < e) __nanosleep(64);
+    __threadfence_system();
+}
+
+static int peer_exchange(omg_hierarchy *h, Level &L, double *v) {
+    PeerState &P = h->peer;
+    int l = (int)(&L - h->lv.data());
+    int q = (v == L.xb) ? 1 : 0;
+    int slot = 2 * l + q;
+    size_t hw = (size_t)L.halo;
+    bool has_dn = g.rank > 0, has_up = g.rank < g.nranks - 1;
+    unsigned long long *ep = P.epochs + slot;
+    unsigned long long *mine = P.flags + 4 * slot;
+    // the flag words I write live in the neighbours' arrays: I am the DN neighbour of `up`, the UP neighbour of `dn`
+    unsigned long long *up_ready = has_up ? P.flags_up + 4 * slot + 0 : nullptr;
+    unsigned long long *dn_ready = has_dn ? P.flags_dn + 4 * slot + 1 : nullptr;
+    unsigned long long *up_done = has_up ? P.flags_up + 4 * slot + 2 : nullptr;
+    unsigned long long *dn_done = has_dn ? P.flags_dn + 4 * slot + 3 : nullptr;
+    cudaStream_t st = g.stream2;
+    k_halo_signal<<<1, 32, 0, st>>>(ep, 1, dn_ready, up_ready);
+    k_halo_spin<<<1, 32, 0, st>>>(ep, has_dn ? mine + 0 : nullptr, has_up ? mine + 1 : nullptr);
+    size_t base_off = (size_t)(v - (q ? L.xb_base : L.xa_base));       // == pad
+    if (has_dn)   // my lower halo <- the top hw owned rows of the lower neighbour
+        CUDA_TRY(cudaMemcpyAsync(v - hw, P.base_dn[slot] + base_off + L.nloc - hw, hw * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+    if (has_up)   // my upper halo <- the bottom hw owned rows of the upper neighbour
+        CUDA_TRY(cudaMemcpyAsync(v + L.nloc, P.base_up[slot] + base_off, hw * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+    k_halo_signal<<<1, 32, 0, st>>>(ep, 0, dn_done, up_done);
+    k_halo_spin<<<1, 32, 0, st>>>(ep, has_dn ? mine + 2 : nullptr, has_up ? mine + 3 : nullptr);
+    h->launches += 4;
+    return OMG_OK;
+}
+
+static int allgather_bytes(const void *mine, void *all_host, size_t bytes) {
+    unsigned char *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, bytes * (size_t)g.nranks));
+    CUDA_TRY(cudaMemcpy(d + bytes * (size_t)g.rank, mine, bytes, cudaMemcpyHostToDevice));
+    NCCL_TRY(nccl.AllGather(d + bytes * (size_t)g.rank, d, bytes, ncclChar, (ncclComm_t)g.nccl_comm, g.stream2));
+    CUDA_TRY(cudaStreamSynchronize(g.stream2));
+    CUDA_TRY(cudaMemcpy(all_host, d, bytes * (size_t)g.nranks, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return OMG_OK;
+}
+
+// Map the neighbours' slab-level buffers and flag words (collective: every rank calls it for the same hierarchy)
+int dist_peer_setup(omg_hierarchy *h) {
+    PeerState &P = h->peer;
+    const char *mode = getenv("OMG_HALO");
+    if (g.nranks == 1 || h->first_replicated == 0 || (mode && strcmp(mode, "nccl") == 0)) return OMG_OK;
+    int nslab = h->first_replicated, nslot = 2 * nslab;
+    CUDA_TRY(cudaMalloc((void **)&P.flags, sizeof(unsigned long long) * 4 * nslot));
+    CUDA_TRY(cudaMalloc((void **)&P.epochs, sizeof(unsigned long long) * nslot));
+    CUDA_TRY(cudaMemset(P.flags, 0, sizeof(unsigned long long) * 4 * nslot));
+    CUDA_TRY(cudaMemset(P.epochs, 0, sizeof(unsigned long long) * nslot));
+    int nh = 1 + nslot;
+    std::vector<cudaIpcMemHandle_t> mine(nh), all((size_t)nh * g.nranks);
+    CUDA_TRY(cudaIpcGetMemHandle(&mine[0], P.flags));
+    for (int l = 0; l < nslab; ++l) {
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[1 + 2 * l], h->lv[l].xa_base));
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[2 + 2 * l], h->lv[l].xb_base));
+    }
+    OMG_TRY(allgather_bytes(mine.data(), all.data(), sizeof(cudaIpcMemHandle_t) * nh));
+    P.base_dn.assign(nslot, nullptr);
+    P.base_up.assign(nslot, nullptr);
+    for (int side = 0; side < 2; ++side) {
+        int peer = side == 0 ? g.rank - 1 : g.rank + 1;
+        if (peer < 0 || peer >= g.nranks) continue;
+        cudaIpcMemHandle_t *ph = &all[(size_t)peer * nh];
+        void *p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, ph[0], cudaIpcMemLazyEnablePeerAccess));
+        P.opened.push_back(p);
+        (side == 0 ? P.flags_dn : P.flags_up) = (unsigned long long *)p;
+        for (int s = 0; s < nslot; ++s) {
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, ph[1 + s], cudaIpcMemLazyEnablePeerAccess));
+            P.opened.push_back(p);
+            (side == 0 ? P.base_dn : P.base_up)[s] = (double *)p;
+        }
+    }
+    // nobody may start signalling before everyone has mapped and zeroed: a barrier over NCCL
+    double *tok = nullptr;
+    CUDA_TRY(cudaMalloc(&tok, sizeof(double)));
+    CUDA_TRY(cudaMemset(tok, 0, sizeof(double)));
+    NCCL_TRY(nccl.AllReduce(tok, tok, 1, ncclFloat64, ncclSum, (ncclComm_t)g.nccl_comm, g.stream2));
+    CUDA_TRY(cudaStreamSynchronize(g.stream2));
+    cudaFree(tok);
+    P.enabled = true;
+    return OMG_OK;
+}
+
+void dist_peer_teardown(omg_hierarchy *h) {
+    PeerState &P = h->peer;
+    for (void *p : P.opened) cudaIpcCloseMemHandle(p);
+    P.opened.clear();
+    if (P.flags) cudaFree(P.flags);
+    if (P.epochs) cudaFree(P.epochs);
+    P.flags = P.epochs = nullptr;
+    P.enabled = false;
+}
+
 // Start filling the halos of vector v (owned pointer) of slab level L: hw elements from each
 // neighbour.  Asynchronous: dist_halo_wait() makes the compute stream wait for it.
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v) {
     if (g.nranks == 1 || !L.slab) return OMG_OK;
     OMG_TRY(comm_fork());
+    if (h->peer.enabled && (v == L.xa || v == L.xb)) {
+        ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0, g.stream2);
+        OMG_TRY(peer_exchange(h, L, v));
+        CUDA_TRY(cudaEventRecord(ev_join, g.stream2));
+        h->halo_pending = true;
+        return OMG_OK;
+    }
     ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0, g.stream2);
     ncclComm_t comm = (ncclComm_t)g.nccl_comm;
     size_t hw = (size_t)L.halo;

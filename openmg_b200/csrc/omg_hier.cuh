@@ -91,8 +91,20 @@ struct ProfRec {
     cudaEvent_t e0, e1;
 };
 
+// Peer-memory halo exchange state (omg_dist.cu): neighbours' level buffers and flag words mapped
+// through CUDA IPC, so halos move with copy-engine peer copies ordered by device-side flags.
+struct PeerState {
+    bool enabled = false;
+    unsigned long long *flags = nullptr;        // local: 4 words per slot {ready<-dn, ready<-up, done<-dn, done<-up}
+    unsigned long long *epochs = nullptr;       // local: one exchange counter per slot
+    unsigned long long *flags_dn = nullptr, *flags_up = nullptr;   // the neighbours' flag arrays (mapped)
+    std::vector<double *> base_dn, base_up;     // per slot: the neighbours' buffer base (mapped), slot = 2*level + (xb?1:0)
+    std::vector<void *> opened;                 // everything cudaIpcOpenMemHandle returned
+};
+
 struct omg_hierarchy {
     int flags = 0;
+    PeerState peer;
     bool profiling = false;          // per-kernel CUDA-event timing (omg_profile_cycle)
     bool halo_pending = false;       // a halo exchange is in flight on the comm stream
     std::vector<ProfRec> prof;
@@ -137,6 +149,8 @@ int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);
 // omg_dist.cu
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v);
 int dist_halo_wait(omg_hierarchy *h);
+int dist_peer_setup(omg_hierarchy *h);
+void dist_peer_teardown(omg_hierarchy *h);
 int dist_allgather(omg_hierarchy *h, const double *piece, double *full, size_t count);
 int dist_allreduce_sum(omg_hierarchy *h, double *v, size_t count);
 void dist_finalize();

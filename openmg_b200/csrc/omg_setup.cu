@@ -1090,6 +1090,8 @@ static int alloc_vectors(omg_hierarchy *h) {
             L.r = L.r_base + L.pad;
         }
     }
+    CUDA_TRY(cudaStreamSynchronize(g.stream));      // buffers are zeroed before any neighbour may write into them
+    OMG_TRY(dist_peer_setup(h));
     h->npartial = std::max(g.sm_count, 1) * 8;
     OMG_TRY(h_alloc_t(h, &h->partial, (size_t)h->npartial, true));
     OMG_TRY(h_alloc_t(h, &h->norm2_dev, 4, true));

@@ -46,7 +46,7 @@ struct St3 {
     int zg0, NZg;          // global index of local plane 0, global planes
     int cz0;               // global index of local coarse plane 0
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
-    int seg_base, nseg, boundary;   // z-segment of a CTA: blockIdx.y + seg_base, or {0, nseg-1} when `boundary`
+    int zlo, zhi, boundary;   // planes [zlo, zhi) in segments of ZL; `boundary`: CTA row 0 -> [0, zlo), row 1 -> [zhi, NZ)
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
 
@@ -95,9 +95,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     constexpr bool XF = (MODE == 2 || MODE == 3);
     const int NS = P.NS;
     const int tid = threadIdx.x;
-    const int seg = P.boundary ? (blockIdx.y == 0 ? 0 : P.nseg - 1) : (int)blockIdx.y + P.seg_base;
-    const int z0 = seg * P.ZL;
-    const int z1 = min(z0 + P.ZL, P.NZ);
+    const int z0 = P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL;
+    const int z1 = P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi);
     const int y0 = blockIdx.x * P.TY;
     const long long span0 = (long long)y0 * P.S1 - P.S1;      // in-plane start of the span (row y0-1)
     const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
@@ -482,12 +481,13 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
         attr_set = true;
     }
     const int chunks = P.NYg / P.TY;
-    P.nseg = (P.NZ + P.ZL - 1) / P.ZL;
-    if (h->halo_pending && P.nseg >= 3) {
-        // interior z-segments do not touch the halo planes: run them while the exchange is in flight
+    const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes
+    if (h->halo_pending && P.NZ >= 4 * ZB + 2) {
+        // interior planes do not touch the halos: run them while the exchange is in flight
         P.boundary = 0;
-        P.seg_base = 1;
-        k_st3<MODE, NT><<<dim3(chunks, P.nseg - 2), NT, smem, g.stream>>>(P);
+        P.zlo = ZB;
+        P.zhi = P.NZ - ZB;
+        k_st3<MODE, NT><<<dim3(chunks, (P.zhi - P.zlo + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
         dist_halo_wait(h);
         P.boundary = 1;
         k_st3<MODE, NT><<<dim3(chunks, 2), NT, smem, g.stream>>>(P);
@@ -495,8 +495,9 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     } else {
         dist_halo_wait(h);
         P.boundary = 0;
-        P.seg_base = 0;
-        k_st3<MODE, NT><<<dim3(chunks, P.nseg), NT, smem, g.stream>>>(P);
+        P.zlo = 0;
+        P.zhi = P.NZ;
+        k_st3<MODE, NT><<<dim3(chunks, (P.NZ + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
     }
     return true;
 }
