@@ -232,20 +232,18 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
     }
     Level &C = h->lv[l + 1];
     bool fused0 = false;
-    if (cur == nullptr && cfg.pre == 1 && cfg.smoother == OMG_SMOOTH_JACOBI && L.regular && !L.slab &&
-        !(h->flags & OMG_FLAG_NO_FUSED)) {
+    if (cur == nullptr && cfg.pre == 1 && cfg.smoother == OMG_SMOOTH_JACOBI && L.regular &&
+        !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_jacobi0_residual_restrict(h, L, C, nullptr, nullptr, nullptr, cfg.omega)) {   // applicability probe
         // zero initial iterate (openmg/__init__.py:191-192): sweep + residual + restriction in one pass over b
-        ProfScope ps(h, "jacobi0_residual_restrict", l, 16.0 * L.nloc + 8.0 * C.nloc);
-        fused0 = stencil_jacobi0_residual_restrict(h, L, C, L.b, L.xa, C.b, cfg.omega);
-        if (fused0) {
-            cur = L.xa;
-            h->launches++;
-        } else if (ps.idx >= 0) {
-            cudaEventDestroy(h->prof.back().e0);
-            cudaEventDestroy(h->prof.back().e1);
-            h->prof.pop_back();
-            ps.idx = -1;
+        dist_halo_exchange(h, L, L.b);
+        {
+            ProfScope ps(h, "jacobi0_residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n);
+            fused0 = stencil_jacobi0_residual_restrict(h, L, C, L.b, L.xa, V(C, C.b), cfg.omega);
         }
+        cur = L.xa;
+        h->launches++;
+        if (L.slab && !C.slab) dist_allgather(h, V(C, C.b) + L.piece_row0, V(C, C.b), (size_t)L.piece_n);
     }
     if (!fused0) {
         cur = launch_smooth(h, L, cfg.smoother, cfg.omega, cfg.pre, cur, L.b);

@@ -171,31 +171,102 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-__global__ void k_halo_signal(unsigned long long *epoch, int bump, unsigned long long *f_dn, unsigned long long *f_up) {
+// "my rows are final" (bump the slot's epoch, tell both neighbours), then wait until theirs are
+__global__ void k_halo_ready(unsigned long long *epoch, unsigned long long *peer_dn, unsigned long long *peer_up,
+                             const unsigned long long *mine_dn, const unsigned long long *mine_up) {
     if (threadIdx.x || blockIdx.x) return;
-    unsigned long long e = *epoch + (unsigned long long)bump;
+    unsigned long long e = *epoch + 1ull;
     *epoch = e;
     __threadfence_system();
-    if (f_dn) st_release_sys(f_dn, e);
-    if (f_up) st_release_sys(f_up, e);
+    if (peer_dn) st_release_sys(peer_dn, e);
+    if (peer_up) st_release_sys(peer_up, e);
+    if (mine_dn)
+        while (ld_acquire_sys(mine_dn) < e) __nanosleep(32);
+    if (mine_up)
+        while (ld_acquire_sys(mine_up) < e) __nanosleep(32);
+    __threadfence_system();
 }
 
-__global__ void k_halo_spin(const unsigned long long *epoch, const unsigned long long *f_dn,
-                            const unsigned long long *f_up) {
+// "I have pulled" to both neighbours, then wait until both have pulled from me
+__global__ void k_halo_done(const unsigned long long *epoch, unsigned long long *peer_dn, unsigned long long *peer_up,
+                            const unsigned long long *mine_dn, const unsigned long long *mine_up) {
     if (threadIdx.x || blockIdx.x) return;
     unsigned long long e = *epoch;
-    if (f_dn)
-        while (ld_acquire_sys(f_dn) < e) __nanosleep(64);
-    if (f_up)
-        while (ld_acquire_sys(f_up) < e) __nanosleep(64);
     __threadfence_system();
+    if (peer_dn) st_release_sys(peer_dn, e);
+    if (peer_up) st_release_sys(peer_up, e);
+    if (mine_dn)
+        while (ld_acquire_sys(mine_dn) < e) __nanosleep(32);
+    if (mine_up)
+        while (ld_acquire_sys(mine_up) < e) __nanosleep(32);
+}
+
+// small halos: the whole exchange in ONE single-CTA kernel (flags, NVLink loads, flags)
+__global__ void __launch_bounds__(1024) k_halo_small(unsigned long long *epoch, unsigned long long *peer_dn_ready,
+                                                     unsigned long long *peer_up_ready,
+                                                     unsigned long long *peer_dn_done, unsigned long long *peer_up_done,
+                                                     const unsigned long long *mine, int has_dn, int has_up,
+                                                     const double2 *__restrict__ src_dn, double2 *__restrict__ dst_lo,
+                                                     const double2 *__restrict__ src_up, double2 *__restrict__ dst_hi,
+                                                     int n2) {
+    __shared__ unsigned long long se;
+    if (threadIdx.x == 0) {
+        unsigned long long e = *epoch + 1ull;
+        *epoch = e;
+        se = e;
+        __threadfence_system();
+        if (has_dn) st_release_sys(peer_dn_ready, e);
+        if (has_up) st_release_sys(peer_up_ready, e);
+        if (has_dn)
+            while (ld_acquire_sys(mine + 0) < e) __nanosleep(32);
+        if (has_up)
+            while (ld_acquire_sys(mine + 1) < e) __nanosleep(32);
+        __threadfence_system();
+    }
+    __syncthreads();
+    // NVLink loads (not cached: ld.cv), 8 in flight per thread
+    for (int side = 0; side < 2; ++side) {
+        const double2 *src = side ? src_up : src_dn;
+        double2 *dst = side ? dst_hi : dst_lo;
+        if (!(side ? has_up : has_dn)) continue;
+        for (int i0 = threadIdx.x; i0 < n2; i0 += 8 * blockDim.x) {
+            double2 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int i = i0 + u * blockDim.x;
+                if (i < n2) t[u] = __ldcv(src + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int i = i0 + u * blockDim.x;
+                if (i < n2) dst[i] = t[u];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long e = se;
+        if (has_dn) st_release_sys(peer_dn_done, e);
+        if (has_up) st_release_sys(peer_up_done, e);
+        if (has_dn)
+            while (ld_acquire_sys(mine + 2) < e) __nanosleep(32);
+        if (has_up)
+            while (ld_acquire_sys(mine + 3) < e) __nanosleep(32);
+    }
+}
+
+static int peer_slot(const Level &L, int l, const double *v) {
+    if (v == L.xa) return 3 * l + 0;
+    if (v == L.xb) return 3 * l + 1;
+    if (v == L.b) return 3 * l + 2;
+    return -1;
 }
 
 static int peer_exchange(omg_hierarchy *h, Level &L, double *v) {
     PeerState &P = h->peer;
     int l = (int)(&L - h->lv.data());
-    int q = (v == L.xb) ? 1 : 0;
-    int slot = 2 * l + q;
+    int slot = peer_slot(L, l, v);
     size_t hw = (size_t)L.halo;
     bool has_dn = g.rank > 0, has_up = g.rank < g.nranks - 1;
     unsigned long long *ep = P.epochs + slot;
@@ -206,18 +277,21 @@ static int peer_exchange(omg_hierarchy *h, Level &L, double *v) {
     unsigned long long *up_done = has_up ? P.flags_up + 4 * slot + 2 : nullptr;
     unsigned long long *dn_done = has_dn ? P.flags_dn + 4 * slot + 3 : nullptr;
     cudaStream_t st = g.stream2;
-    k_halo_signal<<<1, 32, 0, st>>>(ep, 1, dn_ready, up_ready);
-    k_halo_spin<<<1, 32, 0, st>>>(ep, has_dn ? mine + 0 : nullptr, has_up ? mine + 1 : nullptr);
-    size_t base_off = (size_t)(v - (q ? L.xb_base : L.xa_base));       // == pad
-    if (has_dn)   // my lower halo <- the top hw owned rows of the lower neighbour
-        CUDA_TRY(cudaMemcpyAsync(v - hw, P.base_dn[slot] + base_off + L.nloc - hw, hw * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, st));
-    if (has_up)   // my upper halo <- the bottom hw owned rows of the upper neighbour
-        CUDA_TRY(cudaMemcpyAsync(v + L.nloc, P.base_up[slot] + base_off, hw * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, st));
-    k_halo_signal<<<1, 32, 0, st>>>(ep, 0, dn_done, up_done);
-    k_halo_spin<<<1, 32, 0, st>>>(ep, has_dn ? mine + 2 : nullptr, has_up ? mine + 3 : nullptr);
-    h->launches += 4;
+    size_t base_off = (size_t)L.pad;                                    // owned row 0 inside the allocation
+    const double *src_dn = has_dn ? P.base_dn[slot] + base_off + L.nloc - hw : nullptr;   // lower neighbour's top rows
+    const double *src_up = has_up ? P.base_up[slot] + base_off : nullptr;                  // upper neighbour's bottom rows
+    if (hw <= (1u << 15) + 4096 && (hw & 1) == 0) {
+        k_halo_small<<<1, 1024, 0, st>>>(ep, dn_ready, up_ready, dn_done, up_done, mine, has_dn, has_up,
+                                         (const double2 *)src_dn, (double2 *)(v - hw), (const double2 *)src_up,
+                                         (double2 *)(v + L.nloc), (int)(hw / 2));
+        h->launches += 1;
+        return OMG_OK;
+    }
+    k_halo_ready<<<1, 32, 0, st>>>(ep, dn_ready, up_ready, has_dn ? mine + 0 : nullptr, has_up ? mine + 1 : nullptr);
+    if (has_dn) CUDA_TRY(cudaMemcpyAsync(v - hw, src_dn, hw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (has_up) CUDA_TRY(cudaMemcpyAsync(v + L.nloc, src_up, hw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_halo_done<<<1, 32, 0, st>>>(ep, dn_done, up_done, has_dn ? mine + 2 : nullptr, has_up ? mine + 3 : nullptr);
+    h->launches += 2;
     return OMG_OK;
 }
 
@@ -237,7 +311,7 @@ int dist_peer_setup(omg_hierarchy *h) {
     PeerState &P = h->peer;
     const char *mode = getenv("OMG_HALO");
     if (g.nranks == 1 || h->first_replicated == 0 || (mode && strcmp(mode, "nccl") == 0)) return OMG_OK;
-    int nslab = h->first_replicated, nslot = 2 * nslab;
+    int nslab = h->first_replicated, nslot = 3 * nslab;
     CUDA_TRY(cudaMalloc((void **)&P.flags, sizeof(unsigned long long) * 4 * nslot));
     CUDA_TRY(cudaMalloc((void **)&P.epochs, sizeof(unsigned long long) * nslot));
     CUDA_TRY(cudaMemset(P.flags, 0, sizeof(unsigned long long) * 4 * nslot));
@@ -246,8 +320,9 @@ int dist_peer_setup(omg_hierarchy *h) {
     std::vector<cudaIpcMemHandle_t> mine(nh), all((size_t)nh * g.nranks);
     CUDA_TRY(cudaIpcGetMemHandle(&mine[0], P.flags));
     for (int l = 0; l < nslab; ++l) {
-        CUDA_TRY(cudaIpcGetMemHandle(&mine[1 + 2 * l], h->lv[l].xa_base));
-        CUDA_TRY(cudaIpcGetMemHandle(&mine[2 + 2 * l], h->lv[l].xb_base));
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[1 + 3 * l], h->lv[l].xa_base));
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[2 + 3 * l], h->lv[l].xb_base));
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[3 + 3 * l], h->lv[l].b_base));
     }
     OMG_TRY(allgather_bytes(mine.data(), all.data(), sizeof(cudaIpcMemHandle_t) * nh));
     P.base_dn.assign(nslot, nullptr);
@@ -292,7 +367,7 @@ void dist_peer_teardown(omg_hierarchy *h) {
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v) {
     if (g.nranks == 1 || !L.slab) return OMG_OK;
     OMG_TRY(comm_fork());
-    if (h->peer.enabled && (v == L.xa || v == L.xb)) {
+    if (h->peer.enabled && peer_slot(L, 0, v) >= 0) {
         ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0, g.stream2);
         OMG_TRY(peer_exchange(h, L, v));
         CUDA_TRY(cudaEventRecord(ev_join, g.stream2));

@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(OMG_TPB) k_fix_rows(const int *__restrict__ ro
 // fixed-order shuffle reductions.
 __global__ void __launch_bounds__(OMG_TPB) k_fix_crows(const int *__restrict__ crows, int ncrows, BandA<1> A, RegR R,
                                                        const double *__restrict__ x, const double *__restrict__ b,
-                                                       double *__restrict__ rc) {
-    const int crow0 = 0, frow0 = 0;      // global-index pointers
+                                                       double *__restrict__ rc, double xscale) {
+    const int crow0 = 0, frow0 = 0;      // global-index pointers; xscale != 0: x aliases b and x_j = xscale*b_j
     int gt = blockIdx.x * OMG_TPB + threadIdx.x;
     int t = gt >> 5, lane = gt & 31;
     int k = lane >> 2, sub = lane & 3;
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(OMG_TPB) k_fix_crows(const int *__restrict__ c
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (xscale != 0.0) acc *= xscale;
     double r = (valid && sub == 0) ? (__ldg(b + i) - acc) : 0.0;
     r += __shfl_xor_sync(0xffffffffu, r, 4);
     r += __shfl_xor_sync(0xffffffffu, r, 8);
@@ -530,12 +531,13 @@ static void fix_rows(Level &L, Level *C, int mode, const double *xi, const doubl
                                                       V(*C, e), V(L, b), V(L, xo), omega, L.colour, colour);
 }
 
-static void fix_crows(Level &L, const double *x, const double *b, double *rcv) {
+// xscale != 0: x is not read, x_j := xscale * b_j (first sweep from zero with a uniform diagonal)
+static void fix_crows(Level &L, const double *x, const double *b, double *rcv, double xscale = 0.0) {
     int cnt = L.crow_t1 - L.crow_t0;
     if (L.kind != OMG_KIND_BAND_EXC || cnt <= 0) return;
     BandA<1> A{L.band, L.exc_op()};
-    k_fix_crows<<<cdiv((int64_t)cnt * 32, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_crows + L.crow_t0, cnt, A, L.reg,
-                                                                          V(L, x), V(L, b), rcv);
+    k_fix_crows<<<cdiv((int64_t)cnt * 32, OMG_TPB), OMG_TPB, 0, g.stream>>>(
+        L.exc_crows + L.crow_t0, cnt, A, L.reg, xscale != 0.0 ? V(L, b) : V(L, x), V(L, b), rcv, xscale);
 }
 
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
@@ -588,19 +590,21 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
     return true;
 }
 
-// first Jacobi sweep from the zero iterate + residual + restriction, one pass over b (single GPU /
-// replicated levels: across slabs it would need b halos and the neighbour's exception flags)
+// first Jacobi sweep from the zero iterate + residual + restriction, one pass over b.
+// rcv: coarse output indexable by GLOBAL coarse row.  On a slab level b's halos must be valid.
 bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *b, double *xo,
-                                       double *rc, double omega) {
+                                       double *rcv, double omega) {
+    (void)C;
     St3 P{};
     int NT;
-    if (L.slab) return false;
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
+    if (L.slab && L.kind == OMG_KIND_BAND_EXC && !L.exc_diag_uniform) return false;   // halo rows' a_ii unknown here
+    if (!b) return true;       // applicability probe
     P.xi = b;
     P.b = b;
     P.xo = xo;
-    P.rc = rc;
+    P.rc = rcv + L.piece_row0;
     P.w = L.Rw;
     P.omega = omega;
     P.wod = omega / P.d;
@@ -609,7 +613,8 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         P.exc = L.exc_op();
     }
     if (!st3_launch<3>(h, P, NT)) return false;
-    fix_crows(L, xo, b, V(C, rc));
+    // fix-up: x_j = omega b_j / d is recomputed from b when the diagonal is uniform (x's halos are not filled yet)
+    fix_crows(L, xo, b, rcv, L.exc_diag_uniform ? P.wod : 0.0);
     return true;
 }
 
