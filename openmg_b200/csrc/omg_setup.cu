@@ -944,6 +944,161 @@ __global__ void k_gj_unperm(double *__restrict__ M, int n, const int *__restrict
     }
 }
 
+// ---- blocked Gauss-Jordan inversion without pivoting (block 32): 4 launches per 32 columns instead
+// of 5 per column.  Used first; if a diagonal block meets a (near-)zero pivot the pivoted unblocked
+// elimination above is the fallback.  (The Galerkin operators of definite problems need no pivoting.)
+#define BGJ 32
+
+__global__ void k_bgj_pad(double *__restrict__ W, int n, int np) {
+    int i = n + blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i < np) W[(size_t)i * np + i] = 1.0;
+}
+
+// D = inverse of the diagonal block k (in shared memory), written to Dbuf; C = column panel copy
+__global__ void __launch_bounds__(BGJ *BGJ) k_bgj_diag(const double *__restrict__ W, int np, int k,
+                                                        double *__restrict__ Dbuf, int *__restrict__ bad) {
+    __shared__ double S[BGJ][BGJ + 1], V[BGJ][BGJ + 1];
+    int r = threadIdx.y, c = threadIdx.x;
+    S[r][c] = W[(size_t)(k * BGJ + r) * np + k * BGJ + c];
+    V[r][c] = (r == c) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int p = 0; p < BGJ; ++p) {
+        double pv = S[p][p];
+        if (r == 0 && c == 0 && !(fabs(pv) > 1e-280)) *bad = 1;
+        __syncthreads();
+        if (r == p) {
+            S[p][c] = S[p][c] / pv;
+            V[p][c] = V[p][c] / pv;
+        }
+        __syncthreads();
+        double f = S[r][p];
+        __syncthreads();
+        if (r != p) {
+            S[r][c] -= f * S[p][c];
+            V[r][c] -= f * V[p][c];
+        }
+        __syncthreads();
+    }
+    Dbuf[r * BGJ + c] = V[r][c];
+}
+
+__global__ void k_bgj_savecol(const double *__restrict__ W, int np, int k, double *__restrict__ Cbuf) {
+    int i = blockIdx.x * 8 + threadIdx.y, c = threadIdx.x;      // block (32, 8)
+    if (i < np) Cbuf[(size_t)i * BGJ + c] = W[(size_t)i * np + k * BGJ + c];
+}
+
+// row panel: W[K, J] = D * W[K, J] (J != K), W[K, K] = D.  One CTA (32x32) per 32-column tile.
+__global__ void __launch_bounds__(BGJ *BGJ) k_bgj_rowpanel(double *__restrict__ W, int np, int k,
+                                                            const double *__restrict__ Dbuf) {
+    __shared__ double D[BGJ][BGJ + 1], T[BGJ][BGJ + 1];
+    int r = threadIdx.y, c = threadIdx.x, j = blockIdx.x;
+    D[r][c] = Dbuf[r * BGJ + c];
+    double *t = W + (size_t)(k * BGJ + r) * np + j * BGJ + c;
+    T[r][c] = *t;
+    __syncthreads();
+    if (j == k) {
+        *t = D[r][c];
+        return;
+    }
+    double acc = 0.0;
+#pragma unroll 8
+    for (int q = 0; q < BGJ; ++q) acc += D[r][q] * T[q][c];
+    *t = acc;
+}
+
+// trailing update: W[I, J] -= C[I] * W[K, J]   (rows outside block K; for J == K the old value counts as 0,
+// giving W[I, K] = -C[I] * D).  64x64 tile per CTA (16x16 threads, 4x4 outputs each).
+__global__ void __launch_bounds__(256) k_bgj_trailing(double *__restrict__ W, int np, int k,
+                                                       const double *__restrict__ Cbuf) {
+    __shared__ double Cs[64][BGJ + 1], Ps[BGJ][64 + 1];
+    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    for (int t = threadIdx.x; t < 64 * BGJ; t += 256) {
+        int rr = t / BGJ, cc = t % BGJ;
+        Cs[rr][cc] = Cbuf[(size_t)(i0 + rr) * BGJ + cc];
+        int pr = t / 64, pc = t % 64;
+        Ps[pr][pc] = W[(size_t)(k * BGJ + pr) * np + j0 + pc];
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < BGJ; ++q) {
+        double cv[4], pv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) cv[a] = Cs[ty * 4 + a][q];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pv[b] = Ps[q][tx * 4 + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += cv[a] * pv[b];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        int i = i0 + ty * 4 + a;
+        if (i / BGJ == k) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int j = j0 + tx * 4 + b;
+            double *w = W + (size_t)i * np + j;
+            double base = (j / BGJ == k) ? 0.0 : *w;
+            *w = base - acc[a][b];
+        }
+    }
+}
+
+__global__ void k_bgj_copyout(const double *__restrict__ W, int np, int n, double *__restrict__ out) {
+    int j = blockIdx.x * OMG_TPB + threadIdx.x, i = blockIdx.y;
+    if (j < n) out[(size_t)i * n + j] = W[(size_t)i * np + j];
+}
+
+__global__ void k_dense_from_csr_ld(const int *__restrict__ ptr, const int *__restrict__ col,
+                                    const double *__restrict__ val, int n, int ld, double *__restrict__ M) {
+    int i = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i >= n) return;
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) M[(size_t)i * ld + col[p]] += val[p];
+}
+
+// returns OMG_OK with *ok = false when a pivot was unusable (caller falls back)
+static int coarse_factor_blocked(omg_hierarchy *h, Level &L, int n, bool *ok) {
+    int np = (n + 63) / 64 * 64;
+    double *W = nullptr, *Dbuf = nullptr, *Cbuf = nullptr;
+    int *bad = nullptr;
+    OMG_TRY(h_alloc_t(h, &W, (size_t)np * np, true));
+    OMG_TRY(h_alloc_t(h, &Dbuf, (size_t)BGJ * BGJ));
+    OMG_TRY(h_alloc_t(h, &Cbuf, (size_t)np * BGJ));
+    OMG_TRY(h_alloc_t(h, &bad, 1, true));
+    k_dense_from_csr_ld<<<cdiv(n, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.ptr, L.col, L.val, n, np, W);
+    if (np > n) k_bgj_pad<<<cdiv(np - n, OMG_TPB), OMG_TPB, 0, g.stream>>>(W, n, np);
+    int nblk = np / BGJ;
+    for (int k = 0; k < nblk; ++k) {
+        k_bgj_diag<<<1, dim3(BGJ, BGJ), 0, g.stream>>>(W, np, k, Dbuf, bad);
+        k_bgj_savecol<<<cdiv(np, 8), dim3(BGJ, 8), 0, g.stream>>>(W, np, k, Cbuf);
+        k_bgj_rowpanel<<<nblk, dim3(BGJ, BGJ), 0, g.stream>>>(W, np, k, Dbuf);
+        k_bgj_trailing<<<dim3(np / 64, np / 64), 256, 0, g.stream>>>(W, np, k, Cbuf);
+    }
+    k_bgj_copyout<<<dim3(cdiv(n, OMG_TPB), n), OMG_TPB, 0, g.stream>>>(W, np, n, h->Ainv);
+    int b = 0;
+    CUDA_TRY(cudaMemcpyAsync(&b, bad, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaGetLastError());
+    h_free(h, W);
+    h_free(h, Dbuf);
+    h_free(h, Cbuf);
+    h_free(h, bad);
+    *ok = (b == 0);
+    return OMG_OK;
+}
+
+__global__ void k_has_nonfinite(const double *__restrict__ M, size_t count, int *__restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i < count && !isfinite(M[i])) *flag = 1;
+}
+
 static int coarse_factor(omg_hierarchy *h) {
     Level &L = h->lv[h->nlev - 1];
     int n = L.n;
@@ -953,6 +1108,20 @@ static int coarse_factor(omg_hierarchy *h) {
                              "(use more gridLevels / a smaller minSize)", n);
     h->ncoarse = n;
     OMG_TRY(h_alloc_t(h, &h->Ainv, (size_t)n * n, true));
+    if (!getenv("OMG_PIVOTED_FACTOR")) {
+        bool ok = false;
+        OMG_TRY(coarse_factor_blocked(h, L, n, &ok));
+        if (ok) {   // a vanishing pivot can also show up as inf/nan later on: check the result
+            int *flag = nullptr, f = 0;
+            OMG_TRY(h_alloc_t(h, &flag, 1, true));
+            k_has_nonfinite<<<cdiv((int64_t)n * n, OMG_TPB), OMG_TPB, 0, g.stream>>>(h->Ainv, (size_t)n * n, flag);
+            CUDA_TRY(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            CUDA_TRY(cudaStreamSynchronize(g.stream));
+            h_free(h, flag);
+            if (f == 0) return OMG_OK;
+        }
+        CUDA_TRY(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)n * n, g.stream));
+    }
     double *colk = nullptr;
     int *piv = nullptr, *sing = nullptr;
     OMG_TRY(h_alloc_t(h, &colk, (size_t)n));
