@@ -38,7 +38,8 @@ struct St3 {
     int has_exc;
     int nloc;
     int S1, S2, NZ;        // row length, plane size, local planes
-    int TY, NP, SPAN;      // rows per chunk, patches per plane-chunk, span length (TY+2)*S1
+    int TY, NP, SPAN;      // rows per chunk, patches per plane-chunk, staged elements per plane (TY+2)*PITCH
+    int XW, XC, PITCH, XH; // chunk width, chunks per row, staged row pitch (S1, or XW+4), x-halo columns (0 or 2)
     int NS;                // ring stages
     int ZL;                // planes per z-segment (even)
     int cs1, cs2;          // coarse rows per plane, coarse row length
@@ -314,6 +315,271 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     }
 }
 
+// ---------------------------------------------------------------- split-row variant (rows wider than 2*NT)
+//
+// Chunk geometry: TY rows x XW columns.  XW == S1 (full rows): the staged span of a plane is one
+// contiguous piece of the flat vector, one bulk copy.  XW < S1 (rows >= 1024 wide): every staged row
+// is its own bulk copy of XW+4 elements starting 2 elements left of the chunk — in the FLAT vector, so
+// the left/right halo columns of the first/last chunk of a row are the neighbouring rows' ends,
+// exactly the reference's no-boundary-break semantics.
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3x(const St3 P) {
+    constexpr bool SPLIT = true;
+    constexpr int TPT = ST_TPT + 1;   // transform pairs per thread (one more than the full-row kernel)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)P.NS * P.SPAN * sizeof(double));
+    constexpr bool XF = (MODE == 2 || MODE == 3);
+    const int NS = P.NS;
+    const int tid = threadIdx.x;
+    const int z0 = P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL;
+    const int z1 = P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi);
+    const int xc = SPLIT ? (int)blockIdx.x % P.XC : 0, yc = SPLIT ? (int)blockIdx.x / P.XC : (int)blockIdx.x;
+    const int y0 = yc * P.TY, x0 = SPLIT ? xc * P.XW : 0;
+    const int PITCH = SPLIT ? P.PITCH : P.S1;
+    constexpr int XH = SPLIT ? 2 : 0;
+    const long long span0 = (long long)(y0 - 1) * P.S1 + x0 - XH;      // in-plane flat start of staged row 0
+    const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
+
+    auto issue_plane = [&](int slot, int p) {
+        double *dst = stage + (size_t)slot * P.SPAN;
+        const double *src = P.xi + (long long)p * P.S2 + span0;
+        mbar_expect_tx(full + slot, span_bytes);
+        if (!SPLIT) {
+            bulk_g2s(dst, src, span_bytes, full + slot);
+        } else {
+            const uint32_t row_bytes = (uint32_t)PITCH * 8u;
+            for (int q = 0; q < P.TY + 2; ++q)
+                bulk_g2s(dst + q * PITCH, src + (long long)q * P.S1, row_bytes, full + slot);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k < NS; ++k) {
+            int p = z0 - 1 + k;
+            if (p > z1) break;
+            issue_plane(k, p);
+        }
+    }
+
+    // fixed 2x2 patch assignment
+    const int HX = (SPLIT ? P.XW : P.S1) >> 1;
+    int px[ST_PPT], py[ST_PPT];
+    bool act[ST_PPT];
+#pragma unroll
+    for (int k = 0; k < ST_PPT; ++k) {
+        int p = tid + k * NT;
+        act[k] = p < P.NP;
+        p = act[k] ? p : 0;
+        py[k] = p / HX;
+        px[k] = p - py[k] * HX;
+    }
+    double acc[ST_PPT];
+#pragma unroll
+    for (int k = 0; k < ST_PPT; ++k) acc[k] = 0.0;
+
+    // fixed pair assignment of the in-smem transform: staged row and (even) column inside the staged row
+    int tq[TPT], tc[TPT];
+    bool tact[TPT];
+    double aux[TPT];        // MODE 2: e of the pair's coarse cell
+    unsigned auxm[TPT];     // MODE 3: exception mask word of the pair
+    if (XF) {
+        const int HP = PITCH >> 1;
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            int t = tid + k * NT;
+            tact[k] = 2 * t < P.SPAN;
+            t = tact[k] ? t : 0;
+            tq[k] = t / HP;
+            tc[k] = 2 * (t - tq[k] * HP);
+            aux[k] = 0.0;
+            auxm[k] = 0u;
+        }
+    }
+    // flat row (may leave [0,NY) by one) and column of pair k: halo columns of split rows wrap into the
+    // neighbouring flat row
+    auto pair_rc = [&](int k, int &row, int &col) {
+        row = y0 - 1 + tq[k];
+        col = tc[k];
+        if (SPLIT) {
+            int xg = x0 - XH + tc[k];
+            int dq = xg < 0 ? -1 : (xg >= P.S1 ? 1 : 0);
+            row += dq;
+            col = xg - dq * P.S1;
+        }
+    };
+    // aux of local plane p for pair k
+    auto load_aux = [&](int p) {
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            if (!tact[k]) continue;
+            int yy, col;
+            pair_rc(k, yy, col);
+            if (MODE == 2) {
+                int zz = p + P.zg0;
+                if (yy < 0) {              // flat-index wrap into the neighbouring plane
+                    yy += P.NYg;
+                    zz -= 1;
+                } else if (yy >= P.NYg) {
+                    yy -= P.NYg;
+                    zz += 1;
+                }
+                double v = 0.0;
+                if (zz >= 0 && zz < P.NZg)
+                    v = __ldg(P.e + ((long long)((zz >> 1) - P.cz0) * P.cs1 + (yy >> 1)) * P.cs2 + (col >> 1));
+                aux[k] = v;
+            } else if (MODE == 3) {
+                unsigned m = 0u;
+                if (P.has_exc) {
+                    long long gl = (long long)p * P.S2 + (long long)yy * P.S1 + col;
+                    if (gl >= 0 && gl < P.nloc) m = __ldg(P.exc.mask + (gl >> 5));
+                }
+                auxm[k] = m;
+            }
+        }
+    };
+    auto transform = [&](int slot, int p) {
+        double *sp_ = stage + (size_t)slot * P.SPAN;
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            if (!tact[k]) continue;
+            int o = tq[k] * PITCH + tc[k];
+            double2 v = lds2(sp_ + o);
+            if (MODE == 2) {
+                v.x += P.w * aux[k];
+                v.y += P.w * aux[k];
+            } else {
+                double s0 = P.wod, s1 = P.wod;
+                if (P.has_exc) {
+                    unsigned m = auxm[k];
+                    int yy, col;
+                    pair_rc(k, yy, col);
+                    long long gl = (long long)p * P.S2 + (long long)yy * P.S1 + col;
+                    int bit = (int)(gl & 31);
+                    if ((m >> bit) & 3u) {
+                        int base = __ldg(P.exc.wpre + (gl >> 5));
+                        if ((m >> bit) & 1u)
+                            s0 = P.omega / __ldg(P.exc.diag + base + __popc(m & ((1u << bit) - 1u)));
+                        if ((m >> (bit + 1)) & 1u)
+                            s1 = P.omega / __ldg(P.exc.diag + base + __popc(m & ((2u << bit) - 1u)));
+                    }
+                }
+                v.x *= s0;
+                v.y *= s1;
+            }
+            sts2(sp_ + o, v);
+        }
+    };
+
+    if (XF) {
+        // planes z0-1 and z0 are transformed up front, z0+1 inside the loop
+        load_aux(z0 - 1);
+        mbar_wait(full + 0, 0);
+        transform(0, z0 - 1);
+        load_aux(z0);
+        mbar_wait(full + 1, 0);
+        transform(1, z0);
+        load_aux(z0 + 1);
+    }
+
+    for (int z = z0; z < z1; ++z) {
+        const int q = z - (z0 - 1);                // ring position of plane z (plane z0-1 is 0)
+        // b for this plane: issue the loads before blocking on the barrier
+        double2 ba[ST_PPT], bb[ST_PPT];
+#pragma unroll
+        for (int k = 0; k < ST_PPT; ++k) {
+            if (act[k]) {
+                int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + x0 + 2 * px[k];
+                ba[k] = ldg2(P.b + gi);
+                bb[k] = ldg2(P.b + gi + P.S1);
+            }
+        }
+        if (!XF && z == z0) {
+            mbar_wait(full + 0, 0);
+            mbar_wait(full + 1, 0);
+        }
+        {
+            int qq = q + 1;
+            mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
+            if (XF) {
+                transform(qq % NS, z + 1);
+                if (z + 2 <= z1) load_aux(z + 2);
+                __syncthreads();
+            }
+        }
+        const double *sm = stage + (size_t)((q - 1) % NS) * P.SPAN;
+        const double *sc = stage + (size_t)(q % NS) * P.SPAN;
+        const double *sp = stage + (size_t)((q + 1) % NS) * P.SPAN;
+#pragma unroll
+        for (int k = 0; k < ST_PPT; ++k) {
+            if (!act[k]) continue;
+            const int oa = (2 * py[k] + 1) * PITCH + XH + 2 * px[k];
+            const int ob = oa + PITCH;
+            double2 va = lds2(sc + oa), vb = lds2(sc + ob);
+            double2 vn = lds2(sc + oa - PITCH), vs = lds2(sc + ob + PITCH);
+            double2 ma = lds2(sm + oa), mb = lds2(sm + ob);
+            double2 pa = lds2(sp + oa), pb = lds2(sp + ob);
+            double la = sc[oa - 1], ra = sc[oa + 2], lb = sc[ob - 1], rb = sc[ob + 2];
+            double ax0 = P.d * va.x + P.c1 * (la + va.y) + P.cS * (vn.x + vb.x) + P.cP * (ma.x + pa.x);
+            double ax1 = P.d * va.y + P.c1 * (va.x + ra) + P.cS * (vn.y + vb.y) + P.cP * (ma.y + pa.y);
+            double ax2 = P.d * vb.x + P.c1 * (lb + vb.y) + P.cS * (va.x + vs.x) + P.cP * (mb.x + pb.x);
+            double ax3 = P.d * vb.y + P.c1 * (vb.x + rb) + P.cS * (va.y + vs.y) + P.cP * (mb.y + pb.y);
+            const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + x0 + 2 * px[k];
+            if (MODE == 1 || MODE == 3) {
+                double a = acc[k];
+                a += ba[k].x - ax0;
+                a += ba[k].y - ax1;
+                a += bb[k].x - ax2;
+                a += bb[k].y - ax3;
+                if (z & 1) {
+                    int Z = z >> 1;
+                    P.rc[((long long)Z * P.cs1 + (y0 >> 1) + py[k]) * P.cs2 + (x0 >> 1) + px[k]] = P.w * a;
+                    a = 0.0;
+                }
+                acc[k] = a;
+                if (MODE == 3) {
+                    *reinterpret_cast<double2 *>(P.xo + gi) = va;
+                    *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = vb;
+                }
+            } else {
+                double2 oa2, ob2;
+                oa2.x = va.x + P.wod * (ba[k].x - ax0);
+                oa2.y = va.y + P.wod * (ba[k].y - ax1);
+                ob2.x = vb.x + P.wod * (bb[k].x - ax2);
+                ob2.y = vb.y + P.wod * (bb[k].y - ax3);
+                if (P.colour >= 0) {
+                    // two-colour half sweep: colour = (x + y + z) & 1; rows ya and columns x0 + 2px are even
+                    bool even_match = (((z + P.zg0) & 1) == P.colour);    // colour of (ya, x0 + 2px)
+                    if (even_match) {
+                        oa2.y = va.y;
+                        ob2.x = vb.x;
+                    } else {
+                        oa2.x = va.x;
+                        ob2.y = vb.y;
+                    }
+                }
+                *reinterpret_cast<double2 *>(P.xo + gi) = oa2;
+                *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = ob2;
+            }
+        }
+        __syncthreads();        // everyone is done with plane z-1's slot
+        if (tid == 0) {
+            int p = z - 1 + NS;
+            if (p <= z1) {
+                // generic-proxy reads/writes of this slot are ordered before the async-proxy refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_plane((q - 1 + NS) % NS, p);      // == slot of plane z-1
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- fix-ups for exception rows
 
 // xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly).
@@ -411,18 +677,32 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     int NY = S2 / S1, NZ = L.nloc / S2;
     if ((NY & 1) || (NZ & 1) || NZ < 2) return false;
     if (L.pad < S2 + S1) return false;
-    int NT = env_int("OMG_ST_NT", S1 >= 1024 ? 512 : 256);
+    int NT = env_int("OMG_ST_NT", 256);
     if (NT != 256 && NT != 512 && NT != 128) NT = 256;
     if (L.nloc <= (1 << 19)) NT = 128;        // small levels: more, smaller CTAs
+    // chunk width: full rows up to 512 columns per 256 threads, else split rows (largest even divisor)
+    int XW = S1;
+    int maxXW = env_int("OMG_ST_XW", 2 * NT);
+    if (S1 > maxXW && NT == 256) {
+        XW = 0;
+        for (int w = maxXW; w >= 64; w -= 2)
+            if (S1 % w == 0) {
+                XW = w;
+                break;
+            }
+        if (XW == 0) XW = S1;
+    }
+    const int XH = (XW == S1) ? 0 : 2;
+    const int PITCH = (XW == S1) ? S1 : XW + 4;
     // rows per chunk: even, divides NY, patches and transform pairs within the per-thread maxima
-    int maxTY = (4 * NT * ST_PPT) / S1;
+    int maxTY = (4 * NT * ST_PPT) / XW;
     int envTY = env_int("OMG_ST_TY", 0);
     if (envTY > 0) maxTY = std::min(maxTY, envTY);
     if (L.nloc <= (1 << 19)) maxTY = std::min(maxTY, 8);
     int TY = 0;
     for (int t = std::min(maxTY, NY); t >= 2; --t) {
         if ((t & 1) || NY % t != 0) continue;
-        if (xf && (t + 2) * S1 > 2 * NT * ST_TPT) continue;
+        if (xf && (t + 2) * PITCH > 2 * NT * (XH ? ST_TPT + 1 : ST_TPT)) continue;
         TY = t;
         break;
     }
@@ -433,8 +713,12 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->S2 = S2;
     P->NZ = NZ;
     P->TY = TY;
-    P->NP = TY * S1 / 4;
-    P->SPAN = (TY + 2) * S1;
+    P->NP = TY * XW / 4;
+    P->SPAN = (TY + 2) * PITCH;
+    P->XW = XW;
+    P->XC = S1 / XW;
+    P->PITCH = PITCH;
+    P->XH = XH;
     P->NYg = NY;
     P->cs1 = NY / 2;
     P->cs2 = S1 / 2;
@@ -453,7 +737,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     if (NS < 4) return false;
     P->NS = NS;
     // z-segments: even length, aim at ~4 waves of CTAs
-    int chunks = NY / TY;
+    int chunks = (NY / TY) * (S1 / XW);
     int per_sm = NT <= 256 ? 2 : 1;
     int target = std::max(1, (4 * per_sm * std::max(g.sm_count, 1) + chunks - 1) / chunks);
     int ZL = std::max(2, (NZ + target - 1) / target);
@@ -468,46 +752,47 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
 
 static size_t st3_smem(const St3 &P) { return (size_t)P.NS * P.SPAN * sizeof(double) + ST_MAXNS * sizeof(uint64_t); }
 
-template <int MODE, int NT>
+template <int MODE, int NT, bool SPLIT>
 static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     static bool attr_set = false;
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
+    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256> : k_st3<MODE, NT>;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_st3<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         attr_set = true;
     }
-    const int chunks = P.NYg / P.TY;
+    const int chunks = (P.NYg / P.TY) * P.XC;
     const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes
     if (h->halo_pending && P.NZ >= 4 * ZB + 2) {
         // interior planes do not touch the halos: run them while the exchange is in flight
         P.boundary = 0;
         P.zlo = ZB;
         P.zhi = P.NZ - ZB;
-        k_st3<MODE, NT><<<dim3(chunks, (P.zhi - P.zlo + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
+        kern<<<dim3(chunks, (P.zhi - P.zlo + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
         dist_halo_wait(h);
         P.boundary = 1;
-        k_st3<MODE, NT><<<dim3(chunks, 2), NT, smem, g.stream>>>(P);
+        kern<<<dim3(chunks, 2), NT, smem, g.stream>>>(P);
         h->launches++;
     } else {
         dist_halo_wait(h);
         P.boundary = 0;
         P.zlo = 0;
         P.zhi = P.NZ;
-        k_st3<MODE, NT><<<dim3(chunks, (P.NZ + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
+        kern<<<dim3(chunks, (P.NZ + P.ZL - 1) / P.ZL), NT, smem, g.stream>>>(P);
     }
     return true;
 }
 
 template <int MODE>
 static bool st3_launch(omg_hierarchy *h, const St3 &P, int NT) {
-    if (NT == 128) return st3_launch_nt<MODE, 128>(h, P);
-    if (NT == 256) return st3_launch_nt<MODE, 256>(h, P);
-    return st3_launch_nt<MODE, 512>(h, P);
+    if (P.XH) return NT == 256 ? st3_launch_nt<MODE, 256, true>(h, P) : false;     // split rows: 256-thread CTAs only
+    if (NT == 128) return st3_launch_nt<MODE, 128, false>(h, P);
+    if (NT == 256) return st3_launch_nt<MODE, 256, false>(h, P);
+    return st3_launch_nt<MODE, 512, false>(h, P);
 }
 
 static bool regular_matches(const Level &L, const St3 &P) {
