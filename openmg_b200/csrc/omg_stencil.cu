@@ -677,7 +677,9 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     int NY = S2 / S1, NZ = L.nloc / S2;
     if ((NY & 1) || (NZ & 1) || NZ < 2) return false;
     if (L.pad < S2 + S1) return false;
-    int NT = env_int("OMG_ST_NT", 256);
+    // rows up to 512 wide: 256 threads, 2 CTAs/SM; 1024 wide: one 512-thread CTA with full rows (measured equal to
+    // or better than split rows); wider: split rows
+    int NT = env_int("OMG_ST_NT", (S1 > 512 && S1 <= 1024) ? 512 : 256);
     if (NT != 256 && NT != 512 && NT != 128) NT = 256;
     if (L.nloc <= (1 << 19)) NT = 128;        // small levels: more, smaller CTAs
     // chunk width: full rows up to 512 columns per 256 threads, else split rows (largest even divisor)
