@@ -580,6 +580,187 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3x(const St3 P) {
     }
 }
 
+// ================================================================ 2-D structured path
+//
+//   A = d I + c1 (S^1 + S^-1) + cN (S^N + S^-N) + cD (S^(N+1) + S^-(N+1))       (flat index, no row breaks:
+//   openmg/operators.py:221-241 has cN = 0; its Galerkin images have all three pairs)
+// with the closed-form 2x2 restriction.  Same machinery as the 3-D kernel, one dimension down: a CTA owns an
+// x-chunk of XW columns of a y-segment and marches over rows; every row chunk (+2 halo columns each side, taken
+// from the FLAT vector so that row ends continue into the neighbouring rows) is one TMA bulk copy into an
+// mbarrier ring; rows y-1, y, y+1 are resident.  Each thread owns x-pairs; the restriction accumulates a pair
+// over two consecutive rows.
+#define ST2_PP 4           // x-pairs per thread per row (max)
+#define ST2_TPT 5          // staged pairs per thread in the in-smem transform (max)
+#define ST2_NT 256
+
+struct St2 {
+    const double *xi;      // staged vector (MODE 3: b)
+    const double *b;
+    double *xo;
+    double *rc;
+    const double *e;
+    int N, NY;             // row length, local rows
+    int XW, XC, PITCH;     // chunk width, chunks per row, staged row pitch XW + 4
+    int NS, YL;            // ring stages, rows per y-segment (even)
+    int cs;                // coarse row length N/2
+    int yg0, NYg;          // global index of local row 0, global rows
+    int colour, cflat;     // -1: all rows; else the colour relaxed; cflat: colour = x & 1, else (x + y) & 1
+    double d, c1, cN, cD, wod, w;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)P.NS * P.PITCH * sizeof(double));
+    constexpr bool XF = (MODE == 2 || MODE == 3);
+    constexpr int NT = ST2_NT;
+    const int NS = P.NS, PITCH = P.PITCH;
+    const int tid = threadIdx.x;
+    const int x0 = (int)blockIdx.x * P.XW;
+    const int y0 = (int)blockIdx.y * P.YL;
+    const int y1 = min(y0 + P.YL, P.NY);
+    const uint32_t row_bytes = (uint32_t)PITCH * 8u;
+
+    auto issue_row = [&](int slot, int y) {
+        mbar_expect_tx(full + slot, row_bytes);
+        bulk_g2s(stage + (size_t)slot * PITCH, P.xi + (long long)y * P.N + x0 - 2, row_bytes, full + slot);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k < NS; ++k) {
+            int y = y0 - 1 + k;
+            if (y > y1) break;
+            issue_row(k, y);
+        }
+    }
+    const int HXW = P.XW >> 1;       // pairs per row chunk
+    const int HP = PITCH >> 1;       // staged pairs per row
+    double acc[ST2_PP];
+#pragma unroll
+    for (int k = 0; k < ST2_PP; ++k) acc[k] = 0.0;
+    double aux[ST2_TPT];
+#pragma unroll
+    for (int k = 0; k < ST2_TPT; ++k) aux[k] = 0.0;
+
+    // e of the coarse cell of staged pair k of local row y (MODE 2); halo columns wrap into neighbouring flat rows
+    auto load_aux = [&](int y) {
+        if (MODE != 2) return;
+#pragma unroll
+        for (int k = 0; k < ST2_TPT; ++k) {
+            int t = tid + k * NT;
+            if (t >= HP) continue;
+            int xg = x0 - 2 + 2 * t;
+            int dq = xg < 0 ? -1 : (xg >= P.N ? 1 : 0);
+            int row = y + P.yg0 + dq, col = xg - dq * P.N;
+            double v = 0.0;
+            if (row >= 0 && row < P.NYg) v = __ldg(P.e + (long long)((row >> 1) - (P.yg0 >> 1)) * P.cs + (col >> 1));
+            aux[k] = v;
+        }
+    };
+    auto transform = [&](int slot) {
+        double *sp_ = stage + (size_t)slot * PITCH;
+#pragma unroll
+        for (int k = 0; k < ST2_TPT; ++k) {
+            int t = tid + k * NT;
+            if (t >= HP) continue;
+            double2 v = lds2(sp_ + 2 * t);
+            if (MODE == 2) {
+                v.x += P.w * aux[k];
+                v.y += P.w * aux[k];
+            } else {
+                v.x *= P.wod;
+                v.y *= P.wod;
+            }
+            sts2(sp_ + 2 * t, v);
+        }
+    };
+    if (XF) {
+        load_aux(y0 - 1);
+        mbar_wait(full + 0, 0);
+        transform(0);
+        load_aux(y0);
+        mbar_wait(full + 1, 0);
+        transform(1);
+        load_aux(y0 + 1);
+    }
+
+    for (int y = y0; y < y1; ++y) {
+        const int q = y - (y0 - 1);
+        double2 bv[ST2_PP];
+#pragma unroll
+        for (int k = 0; k < ST2_PP; ++k) {
+            int pi = tid + k * NT;
+            if (pi < HXW) bv[k] = ldg2(P.b + (long long)y * P.N + x0 + 2 * pi);
+        }
+        if (!XF && y == y0) {
+            mbar_wait(full + 0, 0);
+            mbar_wait(full + 1, 0);
+        }
+        {
+            int qq = q + 1;
+            mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
+            if (XF) {
+                transform(qq % NS);
+                if (y + 2 <= y1) load_aux(y + 2);
+                __syncthreads();
+            }
+        }
+        const double *sm = stage + (size_t)((q - 1) % NS) * PITCH;
+        const double *sc = stage + (size_t)(q % NS) * PITCH;
+        const double *sp = stage + (size_t)((q + 1) % NS) * PITCH;
+#pragma unroll
+        for (int k = 0; k < ST2_PP; ++k) {
+            int pi = tid + k * NT;
+            if (pi >= HXW) continue;
+            const int o = 2 + 2 * pi;
+            double2 c = lds2(sc + o), m = lds2(sm + o), p = lds2(sp + o);
+            double l = sc[o - 1], r = sc[o + 2], ml = sm[o - 1], pr = sp[o + 2];
+            double ax0 = P.d * c.x + P.c1 * (l + c.y) + P.cN * (m.x + p.x) + P.cD * (ml + p.y);
+            double ax1 = P.d * c.y + P.c1 * (c.x + r) + P.cN * (m.y + p.y) + P.cD * (m.x + pr);
+            const long long gi = (long long)y * P.N + x0 + 2 * pi;
+            if (MODE == 1 || MODE == 3) {
+                double a = acc[k];
+                a += bv[k].x - ax0;
+                a += bv[k].y - ax1;
+                if (y & 1) {
+                    P.rc[(long long)(y >> 1) * P.cs + (x0 >> 1) + pi] = P.w * a;
+                    a = 0.0;
+                }
+                acc[k] = a;
+                if (MODE == 3) *reinterpret_cast<double2 *>(P.xo + gi) = c;
+            } else {
+                double2 o2;
+                o2.x = c.x + P.wod * (bv[k].x - ax0);
+                o2.y = c.y + P.wod * (bv[k].y - ax1);
+                if (P.colour >= 0) {
+                    // x = x0 + 2 pi is even: its colour is 0 (flat parity) or the parity of the global row
+                    bool even_match = P.cflat ? (P.colour == 0) : ((((y + P.yg0) & 1)) == P.colour);
+                    if (even_match)
+                        o2.y = c.y;
+                    else
+                        o2.x = c.x;
+                }
+                *reinterpret_cast<double2 *>(P.xo + gi) = o2;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int yn = y - 1 + NS;
+            if (yn <= y1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_row((q - 1 + NS) % NS, yn);
+            }
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------- fix-ups for exception rows
 
 // xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly).
@@ -827,9 +1008,102 @@ static void fix_crows(Level &L, const double *x, const double *b, double *rcv, d
         L.exc_crows + L.crow_t0, cnt, A, L.reg, xscale != 0.0 ? V(L, b) : V(L, x), V(L, b), rcv, xscale);
 }
 
+// ---------------------------------------------------------------- 2-D host side
+
+static bool st2_params(Level &L, St2 *P, bool need_regular) {
+    if (L.kind == OMG_KIND_CSR || L.slab || g.nranks > 1 && L.slab) return false;
+    const BandOp &B = L.band;
+    int N = 0;
+    double c1 = 0, cN = 0, cD = 0;
+    if (B.nb == 4) {          // {-(N+1), -1, 1, N+1}
+        if (B.off[1] != -1 || B.off[2] != 1 || B.off[0] != -B.off[3]) return false;
+        if (B.coef[1] != B.coef[2] || B.coef[0] != B.coef[3]) return false;
+        N = B.off[3] - 1;
+        c1 = B.coef[2];
+        cD = B.coef[3];
+    } else if (B.nb == 6) {   // {-(N+1), -N, -1, 1, N, N+1}
+        if (B.off[2] != -1 || B.off[3] != 1 || B.off[5] != B.off[4] + 1 || B.off[1] != -B.off[4] ||
+            B.off[0] != -B.off[5])
+            return false;
+        if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;
+        N = B.off[4];
+        c1 = B.coef[3];
+        cN = B.coef[4];
+        cD = B.coef[5];
+    } else
+        return false;
+    if (N < 128 || (N & 1) || L.nloc % N != 0) return false;
+    int NY = L.nloc / N;
+    if ((NY & 1) || NY < 4) return false;
+    if (L.pad < N + 4) return false;
+    if (need_regular && !(L.regular && L.reg.alpha == 2 && L.reg.fs2 == N)) return false;
+    int XW = 0;
+    for (int w = std::min(N, 2 * ST2_NT * ST2_PP); w >= 64; w -= 2)
+        if (N % w == 0) {
+            XW = w;
+            break;
+        }
+    if (XW == 0) return false;
+    if ((XW + 4) / 2 > ST2_NT * ST2_TPT) return false;
+    P->N = N;
+    P->NY = NY;
+    P->XW = XW;
+    P->XC = N / XW;
+    P->PITCH = XW + 4;
+    size_t budget = 113 * 1024;
+    int NS = (int)std::min<size_t>(8, (budget - 64) / ((size_t)P->PITCH * 8));
+    if (NS < 4) return false;
+    P->NS = NS;
+    P->cs = N / 2;
+    P->yg0 = L.row0 / N;
+    P->NYg = L.n / N;
+    P->d = B.diag;
+    P->c1 = c1;
+    P->cN = cN;
+    P->cD = cD;
+    P->colour = -1;
+    P->cflat = L.colour.flat;
+    int target = std::max(1, (8 * std::max(g.sm_count, 1) + P->XC - 1) / P->XC);     // ~4 waves of 2 CTAs/SM
+    int YL = std::max(2, (NY + target - 1) / target);
+    YL += YL & 1;
+    P->YL = std::min(YL, NY);
+    return true;
+}
+
+template <int MODE>
+static bool st2_launch(omg_hierarchy *h, const St2 &P) {
+    static bool attr_set = false;
+    size_t smem = (size_t)P.NS * P.PITCH * sizeof(double) + 8 * sizeof(uint64_t);
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_st2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_set = true;
+    }
+    dist_halo_wait(h);
+    k_st2<MODE><<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
+    return true;
+}
+
+static bool colour2_ok(const Level &L, const St2 &P) {
+    return L.colour.flat || (L.colour.alpha == 2 && L.colour.s2 == P.N);
+}
+
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, false)) {
+        if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+        Q.xi = xi;
+        Q.b = b;
+        Q.xo = xo;
+        Q.wod = omega / Q.d;
+        if (!st2_launch<0>(h, Q)) return false;
+        fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, false)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     P.xi = xi;
@@ -846,6 +1120,17 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
     (void)C;
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, true)) {
+        if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
+        Q.xi = x;
+        Q.b = b;
+        Q.rc = rcv + L.piece_row0;
+        Q.w = L.Rw;
+        if (!st2_launch<1>(h, Q)) return false;
+        fix_crows(L, x, b, rcv);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, false) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
     P.xi = x;
@@ -862,6 +1147,20 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
                             const double *b, double *xo, double omega) {
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, true)) {
+        if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+        if (!xi) return true;
+        Q.xi = xi;
+        Q.b = b;
+        Q.xo = xo;
+        Q.e = e;
+        Q.w = L.Rw;
+        Q.wod = omega / Q.d;
+        if (!st2_launch<2>(h, Q)) return false;
+        fix_rows(L, &C, 2, xi, e, b, xo, omega);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     if (!xi) return true;
@@ -884,6 +1183,20 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
     (void)C;
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, true)) {
+        if (L.kind == OMG_KIND_BAND_EXC && (!L.exc_crows || !L.exc_diag_uniform)) return false;
+        if (!b) return true;
+        Q.xi = b;
+        Q.b = b;
+        Q.xo = xo;
+        Q.rc = rcv + L.piece_row0;
+        Q.w = L.Rw;
+        Q.wod = omega / Q.d;
+        if (!st2_launch<3>(h, Q)) return false;
+        fix_crows(L, xo, b, rcv, Q.wod);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_crows) return false;
     if (L.slab && L.kind == OMG_KIND_BAND_EXC && !L.exc_diag_uniform) return false;   // halo rows' a_ii unknown here
@@ -913,6 +1226,18 @@ static bool grid_colour_matches(const Level &L, const St3 &P) {
 bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *xi, const double *b, double *xo) {
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, false) && colour2_ok(L, Q)) {
+        if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+        Q.xi = xi;
+        Q.b = b;
+        Q.xo = xo;
+        Q.wod = 1.0 / Q.d;
+        Q.colour = colour;
+        if (!st2_launch<0>(h, Q)) return false;
+        fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, false) || !grid_colour_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     P.xi = xi;
@@ -930,6 +1255,21 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
                                   const double *e, const double *b, double *xo) {
     St3 P{};
     int NT;
+    St2 Q{};
+    if (st2_params(L, &Q, true) && colour2_ok(L, Q)) {
+        if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
+        if (!xi) return true;
+        Q.xi = xi;
+        Q.b = b;
+        Q.xo = xo;
+        Q.e = e;
+        Q.w = L.Rw;
+        Q.wod = 1.0 / Q.d;
+        Q.colour = colour;
+        if (!st2_launch<2>(h, Q)) return false;
+        fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
+        return true;
+    }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P) || !grid_colour_matches(L, P)) return false;
     if (L.kind == OMG_KIND_BAND_EXC && !L.exc_rows) return false;
     if (!xi) return true;
