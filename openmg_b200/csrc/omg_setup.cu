@@ -1196,6 +1196,7 @@ static int alloc_vectors(omg_hierarchy *h) {
                     reach2[l] = a;
             }
         L.pad = (2 * reach[l] + 15) / 16 * 16;    // the 2.5-D stencil path stages plane -1 with its halo rows
+        if (L.kind != OMG_KIND_CSR && L.band.nb == 2 && L.n >= 512) L.pad = std::max(L.pad, 2048 + 16);   // 1-D rows view
     }
     // ---- slab partition (multi-GPU): row0 / nloc per level
     std::vector<int64_t> lead(nlev), rows(nlev), row0(nlev), nloc(nlev);

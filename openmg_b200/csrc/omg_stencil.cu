@@ -605,6 +605,7 @@ struct St2 {
     int cs;                // coarse row length N/2
     int yg0, NYg;          // global index of local row 0, global rows
     int colour, cflat;     // -1: all rows; else the colour relaxed; cflat: colour = x & 1, else (x + y) & 1
+    int oned;              // 1-D problem viewed as rows of N: restriction pairs x only, coarse row length N/2 per row
     double d, c1, cN, cD, wod, w;
 };
 
@@ -659,7 +660,10 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
             int dq = xg < 0 ? -1 : (xg >= P.N ? 1 : 0);
             int row = y + P.yg0 + dq, col = xg - dq * P.N;
             double v = 0.0;
-            if (row >= 0 && row < P.NYg) v = __ldg(P.e + (long long)((row >> 1) - (P.yg0 >> 1)) * P.cs + (col >> 1));
+            if (row >= 0 && row < P.NYg) {
+                long long crow = P.oned ? (long long)(row - P.yg0) : (long long)((row >> 1) - (P.yg0 >> 1));
+                v = __ldg(P.e + crow * P.cs + (col >> 1));
+            }
             aux[k] = v;
         }
     };
@@ -728,7 +732,10 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
                 double a = acc[k];
                 a += bv[k].x - ax0;
                 a += bv[k].y - ax1;
-                if (y & 1) {
+                if (P.oned) {
+                    P.rc[(long long)y * P.cs + (x0 >> 1) + pi] = P.w * a;
+                    a = 0.0;
+                } else if (y & 1) {
                     P.rc[(long long)(y >> 1) * P.cs + (x0 >> 1) + pi] = P.w * a;
                     a = 0.0;
                 }
@@ -1015,7 +1022,18 @@ static bool st2_params(Level &L, St2 *P, bool need_regular) {
     const BandOp &B = L.band;
     int N = 0;
     double c1 = 0, cN = 0, cD = 0;
-    if (B.nb == 4) {          // {-(N+1), -1, 1, N+1}
+    bool oned = false;
+    if (B.nb == 2) {          // 1-D {-1, 1}: view the vector as rows of N (any even divisor): flat semantics are the same
+        if (B.off[0] != -1 || B.off[1] != 1 || B.coef[0] != B.coef[1]) return false;
+        for (int w = 2048; w >= 128; w >>= 1)
+            if (L.nloc % w == 0 && L.nloc / w >= 4) {
+                N = w;
+                break;
+            }
+        if (N == 0) return false;
+        c1 = B.coef[1];
+        oned = true;
+    } else if (B.nb == 4) {          // {-(N+1), -1, 1, N+1}
         if (B.off[1] != -1 || B.off[2] != 1 || B.off[0] != -B.off[3]) return false;
         if (B.coef[1] != B.coef[2] || B.coef[0] != B.coef[3]) return false;
         N = B.off[3] - 1;
@@ -1034,9 +1052,11 @@ static bool st2_params(Level &L, St2 *P, bool need_regular) {
         return false;
     if (N < 128 || (N & 1) || L.nloc % N != 0) return false;
     int NY = L.nloc / N;
-    if ((NY & 1) || NY < 4) return false;
+    if ((!oned && (NY & 1)) || NY < 4) return false;
     if (L.pad < N + 4) return false;
-    if (need_regular && !(L.regular && L.reg.alpha == 2 && L.reg.fs2 == N)) return false;
+    if (need_regular && !oned && !(L.regular && L.reg.alpha == 2 && L.reg.fs2 == N)) return false;
+    if (need_regular && oned && !(L.regular && L.reg.alpha == 1)) return false;
+    P->oned = oned ? 1 : 0;
     int XW = 0;
     for (int w = std::min(N, 2 * ST2_NT * ST2_PP); w >= 64; w -= 2)
         if (N % w == 0) {
@@ -1087,7 +1107,7 @@ static bool st2_launch(omg_hierarchy *h, const St2 &P) {
 }
 
 static bool colour2_ok(const Level &L, const St2 &P) {
-    return L.colour.flat || (L.colour.alpha == 2 && L.colour.s2 == P.N);
+    return L.colour.flat || (!P.oned && L.colour.alpha == 2 && L.colour.s2 == P.N);
 }
 
 bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo, double omega) {
