@@ -466,10 +466,9 @@ __global__ void __launch_bounds__(OMG_TPB) k_galerkin(ARows A, RMap M, int clo, 
             ++m2;
         }
     }
-    if (!WRITE) {
+    if constexpr (!WRITE) {
         ocnt[I] = m2;
-        return;
-    }
+    } else {
     for (int a = 1; a < m2; ++a) {   // insertion sort by column
         int kJ = sJ[(size_t)a * B + r];
         double kV = sV[(size_t)a * B + r];
@@ -486,6 +485,7 @@ __global__ void __launch_bounds__(OMG_TPB) k_galerkin(ARows A, RMap M, int clo, 
     for (int t = 0; t < m2; ++t) {
         ocol[o + t] = sJ[(size_t)t * B + r];
         oval[o + t] = sV[(size_t)t * B + r];
+    }
     }
 }
 

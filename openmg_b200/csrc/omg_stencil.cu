@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
 
     // e of the coarse cell of staged pair k of local row y (MODE 2); halo columns wrap into neighbouring flat rows
     auto load_aux = [&](int y) {
-        if (MODE != 2) return;
+        if constexpr (MODE == 2) {
 #pragma unroll
         for (int k = 0; k < ST2_TPT; ++k) {
             int t = tid + k * NT;
@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
                 v = __ldg(P.e + crow * P.cs + (col >> 1));
             }
             aux[k] = v;
+        }
         }
     };
     auto transform = [&](int slot) {
@@ -1018,7 +1019,7 @@ static void fix_crows(Level &L, const double *x, const double *b, double *rcv, d
 // ---------------------------------------------------------------- 2-D host side
 
 static bool st2_params(Level &L, St2 *P, bool need_regular) {
-    if (L.kind == OMG_KIND_CSR || L.slab || g.nranks > 1 && L.slab) return false;
+    if (L.kind == OMG_KIND_CSR || L.slab) return false;      // slab levels: the generic kernels (3-D has its own slab path)
     const BandOp &B = L.band;
     int N = 0;
     double c1 = 0, cN = 0, cD = 0;

@@ -268,3 +268,45 @@ def test_converged_solution_matches_reference_gs():
     rate = (hist[7] / hist[2]) ** (1 / 5.0)
     assert rate < 0.2                    # reference lex GS: ~0.04 per cycle; 2-colour: ~0.03
     h.close()
+
+
+def test_split_row_and_tiling_variants_agree(monkeypatch):
+    """The stencil kernel's tiling knobs (debug environment variables read at launch time) select other
+    code paths — split rows with per-row TMA copies, 512-thread CTAs, deeper rings — which must all give
+    the same iterates as the default tiling."""
+    shape, gl = (128, 128, 128), 4
+    A = omg.operators.poisson_band(shape)
+    u = np.random.RandomState(0).random_sample(A.n)
+    ref = None
+    for env in ({}, {"OMG_ST_XW": "64"}, {"OMG_ST_NT": "512"}, {"OMG_ST_NT": "128", "OMG_ST_TY": "4"},
+                {"OMG_ST_NS": "4", "OMG_ST_ZL": "6"}):
+        for k in ("OMG_ST_XW", "OMG_ST_NT", "OMG_ST_TY", "OMG_ST_NS", "OMG_ST_ZL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = Hierarchy(A, shape, gl - 1, 8)
+        b = h.matvec(u, 0)
+        outs = [h.solve(b, None, 1, 1, sm, 0.8, 3, 0.0)[0] for sm in ("jacobi", "rbgs")]
+        h.close()
+        if ref is None:
+            ref = outs
+        else:
+            for a, r in zip(outs, ref):
+                close(a, r, 1e-13, "tiling %r" % (env,))
+
+
+def test_structured_2d_and_1d_paths_vs_generic():
+    """2-D and 1-D band levels run on the row-marching TMA kernel; OMG_FLAG_NO_FUSED forces the generic
+    kernels: same iterates, Jacobi and two-colour."""
+    for shape, gl, s1 in (((512, 512), 4, False), ((1 << 18,), 9, True)):
+        A = omg.operators.poisson_band(shape, sparse_1d=s1)
+        u = np.random.RandomState(1).random_sample(A.n)
+        res = {}
+        for flags in (0, _lib.FLAG_NO_FUSED):
+            h = Hierarchy(A, shape, gl - 1, 8, flags=flags)
+            b = h.matvec(u, 0)
+            res[flags] = [h.solve(b, None, pre, post, sm, 0.8, 3, 0.0)[0]
+                          for sm in ("jacobi", "rbgs") for (pre, post) in ((1, 1), (2, 0))]
+            h.close()
+        for a, r in zip(res[0], res[_lib.FLAG_NO_FUSED]):
+            close(a, r, 1e-13, "structured vs generic %r" % (shape,))
