@@ -310,3 +310,53 @@ def test_structured_2d_and_1d_paths_vs_generic():
             h.close()
         for a, r in zip(res[0], res[_lib.FLAG_NO_FUSED]):
             close(a, r, 1e-13, "structured vs generic %r" % (shape,))
+
+
+def test_general_sparse_matrix_csr_path():
+    """An arbitrary (non-Poisson, non-dyadic, unsorted, with explicit zeros and duplicates) coefficient
+    matrix: every level is generic CSR.  Galerkin patterns bit-exact, values to rounding, cycles vs oracle."""
+    rs = np.random.RandomState(11)
+    for pshape, gl in (((64, 64), 2), ((512,), 3), ((8, 8, 8), 1)):
+        n = int(np.prod(pshape))
+        M = sp.random(n, n, density=6.0 / n, random_state=rs, format="coo")
+        M = M + M.T + sp.diags(np.full(n, 20.0) + rs.random_sample(n))
+        M = sp.coo_matrix(M)
+        perm = rs.permutation(M.nnz)                       # unsorted COO with a few explicit zeros / duplicates
+        rows = np.concatenate([M.row[perm], [0, 1, 1]])
+        cols = np.concatenate([M.col[perm], [n - 1, 2, 2]])
+        vals = np.concatenate([M.data[perm], [0.0, 0.25, -0.25]])
+        A_in = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))   # duplicates summed by scipy on conversion
+        A_ref = sp.csr_matrix(A_in)
+        R = orc.restrictionList(pshape, gl - 1, 8)
+        Aor = orc.coeffecientList(A_ref, R)
+        h = Hierarchy(A_in, pshape, gl - 1, 8)
+        assert h.nlevels == len(Aor)
+        for l in range(1, h.nlevels):
+            got, want = h.export_A(l), orc.canonical_csr(Aor[l])
+            assert h.level_info(l)["kind"] == "csr"
+            np.testing.assert_array_equal(got.indptr, want.indptr)
+            np.testing.assert_array_equal(got.indices, want.indices)
+            np.testing.assert_allclose(got.data, want.data, rtol=1e-13, atol=1e-15)
+        u, b = seeded_problem(A_ref)
+        params = {'coarsestLevel': len(R), 'preIterations': 1, 'postIterations': 1, 'verbose': False}
+        for smoother, tol in (("jacobi", JAC_RTOL), ("rbgs", RB_RTOL), ("gs", 1e-11)):
+            sm = orc.make_smoother(smoother, pshape, 0.8)
+            xo = None
+            for _ in range(3):
+                xo, info = orc.mgCycle(Aor, b, 0, R, params, initial=xo, smooth=sm)
+            x, cyc, norm, hist = h.solve(b, None, 1, 1, smoother, 0.8, 3, 0.0, want_history=True)
+            close(x, xo, tol, "general matrix %r %s" % (pshape, smoother))
+            assert abs(norm - info['norm']) <= 1e-9 * max(info['norm'], 1e-30) + 1e-12
+        h.close()
+
+
+def test_dense_and_matrix_inputs():
+    """ndarray / np.matrix / COO / CSC inputs and (N,1) right-hand sides give the same result as CSR."""
+    shape = (16, 16)
+    A = orc.poisson_csr(shape)
+    u, b = seeded_problem(A)
+    ref = omg.mgSolve(A, b, {'problemShape': shape, 'gridLevels': 2, 'cycles': 3, 'smoother': 'jacobi'})
+    for Ain, bb in ((A.toarray(), b), (np.asmatrix(A.toarray()), b.reshape(-1, 1)), (A.tocoo(), b), (A.tocsc(), b)):
+        x = omg.mgSolve(Ain, bb, {'problemShape': shape, 'gridLevels': 2, 'cycles': 3, 'smoother': 'jacobi'})
+        assert x.shape == (256,)
+        np.testing.assert_array_equal(x, ref)
