@@ -927,14 +927,32 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     if (envNS >= 4) NS = std::min(NS, envNS);
     if (NS < 4) return false;
     P->NS = NS;
-    // z-segments: even length, aim at ~4 waves of CTAs
+    // z-segments (even length).  Two losses to balance: every segment re-stages 2 halo planes and ramps its
+    // pipeline (~2.5 planes of dead time), and a grid that is not a whole number of waves of resident CTAs leaves
+    // SMs idle in the last wave.  Pick the segment count that maximises ZL/(ZL+2.5) * CTAs/(waves*slots).
     int chunks = (NY / TY) * (S1 / XW);
-    int per_sm = NT <= 256 ? 2 : 1;
-    int target = std::max(1, (4 * per_sm * std::max(g.sm_count, 1) + chunks - 1) / chunks);
-    int ZL = std::max(2, (NZ + target - 1) / target);
-    ZL = std::max(ZL, env_int("OMG_ST_ZL", 0));
-    ZL += ZL & 1;
-    ZL = std::min(ZL, NZ);
+    int per_sm = NT <= 128 ? 4 : (NT <= 256 ? 2 : 1);
+    int slots = per_sm * std::max(g.sm_count, 1);
+    int ZL = NZ;
+    double best = -1.0;
+    for (int nseg = 1; nseg <= NZ / 2; ++nseg) {
+        int zl = (NZ + nseg - 1) / nseg;
+        zl += zl & 1;
+        int ns = (NZ + zl - 1) / zl;
+        long long ctas = (long long)chunks * ns;
+        long long waves = (ctas + slots - 1) / slots;
+        if (waves > 6) break;
+        double eff = (zl / (zl + 2.5)) * ((double)ctas / (double)(waves * slots));
+        if (eff > best + 1e-9) {
+            best = eff;
+            ZL = zl;
+        }
+    }
+    {
+        int envZL = env_int("OMG_ST_ZL", 0);
+        if (envZL >= 2) ZL = envZL + (envZL & 1);
+    }
+    ZL = std::min(std::max(ZL, 2), NZ);
     P->ZL = ZL;
     P->has_exc = 0;
     P->colour = -1;
@@ -1084,10 +1102,25 @@ static bool st2_params(Level &L, St2 *P, bool need_regular) {
     P->cD = cD;
     P->colour = -1;
     P->cflat = L.colour.flat;
-    int target = std::max(1, (8 * std::max(g.sm_count, 1) + P->XC - 1) / P->XC);     // ~4 waves of 2 CTAs/SM
-    int YL = std::max(2, (NY + target - 1) / target);
-    YL += YL & 1;
-    P->YL = std::min(YL, NY);
+    {   // y-segments: same trade-off as the z-segments of the 3-D kernel
+        int slots = 2 * std::max(g.sm_count, 1);
+        int YL = NY;
+        double best = -1.0;
+        for (int nseg = 1; nseg <= NY / 2; ++nseg) {
+            int yl = (NY + nseg - 1) / nseg;
+            yl += yl & 1;
+            int ns = (NY + yl - 1) / yl;
+            long long ctas = (long long)P->XC * ns;
+            long long waves = (ctas + slots - 1) / slots;
+            if (waves > 6) break;
+            double eff = (yl / (yl + 2.5)) * ((double)ctas / (double)(waves * slots));
+            if (eff > best + 1e-9) {
+                best = eff;
+                YL = yl;
+            }
+        }
+        P->YL = std::min(std::max(YL, 2), NY);
+    }
     return true;
 }
 
