@@ -271,8 +271,8 @@ def ours(args):
         ms, launches = h.bench_cycles(args.steps, args.pre, args.post, args.smoother, 0.8)
         barrier()
         ms = allmax(ms)                     # identical on every rank from here on (collectives must match)
-        if ms < 600:   # keep the GPU under the same load a little longer so the sampler sees it
-            h.bench_cycles(max(args.steps, int(600 / max(ms / args.steps, 1e-3))), args.pre, args.post,
+        if ms < 1500:   # keep the GPU under the same load a little longer so the sampler sees it
+            h.bench_cycles(max(args.steps, int(1500 / max(ms / args.steps, 1e-3))), args.pre, args.post,
                            args.smoother, 0.8)
     clocks = cs.summary()
     final_norm = h.current_norm()
