@@ -29,6 +29,18 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_ctypes_table_matches_header_prototypes():
+    """Every prototype of include/omg_b200.h has the same number of parameters as its ctypes signature."""
+    src = open(os.path.join(ROOT, "include", "omg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|void|const char \*)\s*(omg_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_product_path_fails_loudly_without_device():
     import ctypes
     lib = _lib.load()
