@@ -59,6 +59,18 @@ struct RegR {
     double w;                // 1/2^alpha
 };
 
+// Positional stencil classes of a 3-D Galerkin level.  The reference's operators have no boundary breaks, so their
+// Galerkin images deviate from the interior stencil exactly on the x- and y-boundaries of the grid, and all rows of
+// one position class (cx, cy in {first, interior, last}) share one row pattern.  A class is stored as the
+// correction taps (row entry minus band entry); class index = 3*cy + cx, class 4 is the interior (no taps).
+#define OMG_CLS_TAPS 6
+struct ClsTab {
+    int ntap[9];
+    int soff[9][OMG_CLS_TAPS];     // offset inside the plane (flat, may reach the +-1 halo rows)
+    int dz[9][OMG_CLS_TAPS];       // plane offset -1, 0, +1
+    double coef[9][OMG_CLS_TAPS];
+};
+
 // two-colouring rule of a level (oracle.colouring)
 struct ColourRule {
     int flat;                // 1: colour = i & 1

@@ -44,6 +44,8 @@ struct Level {
     int *exc_crows = nullptr;    // coarse rows whose aggregate contains an exception row (regular R)
     int nexc_crows = 0;
     bool exc_diag_uniform = true; // every exception row has a_ii == band.diag
+    bool classed = false;         // all exception rows follow the 9 positional stencil classes below
+    ClsTab cls{};
     // full CSR (sorted columns, global indices == local on one GPU); may be absent for a band level 0
     int64_t nnz = 0;
     int *ptr = nullptr, *col = nullptr;

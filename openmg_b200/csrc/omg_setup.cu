@@ -685,6 +685,144 @@ __global__ void k_diag_differs(const double *__restrict__ ediag, int nexc, doubl
     if (s < nexc && ediag[s] != d) *flag = 1;
 }
 
+// ---- positional stencil classes (3-D Galerkin levels)
+
+struct ClsFlat {     // host/device helper: flat offsets + deltas per class
+    int ntap[9];
+    int off[9][OMG_CLS_TAPS];
+    double coef[9][OMG_CLS_TAPS];
+};
+
+// Every row must equal band + class correction (truncated to [0,n), exact zeros absent); interior-class rows must
+// not be exception rows.  One thread per row.
+__global__ void __launch_bounds__(OMG_TPB) k_check_classes(const int *__restrict__ ptr, const int *__restrict__ col,
+                                                           const double *__restrict__ val, const unsigned *__restrict__ mask,
+                                                           int n, BandOp b, ClsFlat c, int S1, int NY,
+                                                           int *__restrict__ bad) {
+    int i = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i >= n) return;
+    int x = i % S1, y = (i / S1) % NY;
+    int cls = 3 * (y == 0 ? 0 : (y == NY - 1 ? 2 : 1)) + (x == 0 ? 0 : (x == S1 - 1 ? 2 : 1));
+    bool exc = (mask[i >> 5] >> (i & 31)) & 1u;
+    if (cls == 4) {
+        if (exc) *bad = 1;
+        return;
+    }
+    if (!exc && c.ntap[cls] == 0) return;
+    // expected value at flat offset o
+    auto expected = [&](int o, bool &known) {
+        double v = 0.0;
+        known = false;
+        if (o == 0) {
+            v = b.diag;
+            known = true;
+        }
+        for (int k = 0; k < b.nb; ++k)
+            if (b.off[k] == o) {
+                v += b.coef[k];
+                known = true;
+            }
+        for (int t = 0; t < c.ntap[cls]; ++t)
+            if (c.off[cls][t] == o) {
+                v += c.coef[cls][t];
+                known = true;
+            }
+        return v;
+    };
+    int seen = 0;
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) {
+        bool known;
+        double v = expected(col[p] - i, known);
+        if (!known || v != val[p]) {
+            *bad = 1;
+            return;
+        }
+        ++seen;
+    }
+    // no expected nonzero in-range entry may be missing
+    int want = 0;
+    bool known;
+    if (expected(0, known) != 0.0) ++want;
+    for (int k = 0; k < b.nb; ++k) {
+        int j = i + b.off[k];
+        if (j >= 0 && j < n && expected(b.off[k], known) != 0.0) ++want;
+    }
+    for (int t = 0; t < c.ntap[cls]; ++t) {
+        int o = c.off[cls][t];
+        bool in_band = (o == 0);
+        for (int k = 0; k < b.nb; ++k) in_band = in_band || b.off[k] == o;
+        int j = i + o;
+        if (!in_band && j >= 0 && j < n && expected(o, known) != 0.0) ++want;
+    }
+    if (want != seen) *bad = 1;
+}
+
+static int detect_classes(omg_hierarchy *h, Level &L) {
+    L.classed = false;
+    if (L.kind != OMG_KIND_BAND_EXC || L.band.nb != 6 || !L.ptr || getenv("OMG_NO_CLASSES")) return OMG_OK;
+    const BandOp &B = L.band;
+    if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return OMG_OK;
+    int S1 = B.off[4], S2 = B.off[5];
+    if (S1 < 8 || S2 % S1 != 0 || L.n % S2 != 0) return OMG_OK;
+    int NY = S2 / S1, NZ = L.n / S2;
+    if (NY < 4 || NZ < 3) return OMG_OK;
+    ClsFlat cf{};
+    std::vector<int> hp(2);
+    for (int cy = 0; cy < 3; ++cy)
+        for (int cx = 0; cx < 3; ++cx) {
+            int cls = 3 * cy + cx;
+            cf.ntap[cls] = 0;
+            if (cls == 4) continue;
+            int x = cx == 0 ? 0 : (cx == 2 ? S1 - 1 : S1 / 2);
+            int y = cy == 0 ? 0 : (cy == 2 ? NY - 1 : NY / 2);
+            int r = (NZ / 2) * S2 + y * S1 + x;
+            CUDA_TRY(cudaMemcpy(hp.data(), L.ptr + r, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            int len = hp[1] - hp[0];
+            if (len <= 0 || len > 32) return OMG_OK;
+            std::vector<int> hc(len);
+            std::vector<double> hv(len);
+            CUDA_TRY(cudaMemcpy(hc.data(), L.col + hp[0], len * sizeof(int), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hv.data(), L.val + hp[0], len * sizeof(double), cudaMemcpyDeviceToHost));
+            // delta = row - band over the union of offsets
+            std::map<int, double> delta;
+            for (int t = 0; t < len; ++t) delta[hc[t] - r] += hv[t];
+            delta[0] -= B.diag;
+            for (int k = 0; k < B.nb; ++k) delta[B.off[k]] -= B.coef[k];
+            for (auto &kv : delta) {
+                if (kv.second == 0.0) continue;
+                if (kv.first == 0) return OMG_OK;                 // classes need a uniform diagonal
+                int o = kv.first;
+                int dz = o > S2 / 2 ? 1 : (o < -S2 / 2 ? -1 : 0);
+                int so = o - dz * S2;
+                if (so < -(S1 + 1) || so > S1 + 1) return OMG_OK;  // outside the staged +-1 rows
+                if (cf.ntap[cls] >= OMG_CLS_TAPS) return OMG_OK;
+                cf.off[cls][cf.ntap[cls]] = o;
+                cf.coef[cls][cf.ntap[cls]] = kv.second;
+                cf.ntap[cls]++;
+            }
+        }
+    int *bad = nullptr, hb = 0;
+    OMG_TRY(h_alloc_t(h, &bad, 1, true));
+    k_check_classes<<<cdiv(L.n, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.ptr, L.col, L.val, L.exc_mask, L.n, B, cf, S1, NY, bad);
+    CUDA_TRY(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaGetLastError());
+    h_free(h, bad);
+    if (hb) return OMG_OK;
+    for (int c = 0; c < 9; ++c) {
+        L.cls.ntap[c] = cf.ntap[c];
+        for (int t = 0; t < cf.ntap[c]; ++t) {
+            int o = cf.off[c][t];
+            int dz = o > S2 / 2 ? 1 : (o < -S2 / 2 ? -1 : 0);
+            L.cls.dz[c][t] = dz;
+            L.cls.soff[c][t] = o - dz * S2;
+            L.cls.coef[c][t] = cf.coef[c][t];
+        }
+    }
+    L.classed = true;
+    return OMG_OK;
+}
+
 static int detect_band(omg_hierarchy *h, Level &L) {
     L.kind = OMG_KIND_CSR;
     if (h->flags & OMG_FLAG_FORCE_CSR) return OMG_OK;
@@ -803,7 +941,7 @@ static int detect_band(omg_hierarchy *h, Level &L) {
         h_free(h, cmask);
         h_free(h, cpre);
     }
-    return OMG_OK;
+    return detect_classes(h, L);
 }
 
 // ------------------------------------------------------------------ band -> CSR (export of a band-only level 0)

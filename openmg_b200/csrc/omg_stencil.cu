@@ -48,6 +48,8 @@ struct St3 {
     int cz0;               // global index of local coarse plane 0
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
     int zlo, zhi, boundary;   // planes [zlo, zhi) in segments of ZL; `boundary`: CTA row 0 -> [0, zlo), row 1 -> [zhi, NZ)
+    int use_cls;           // rows on the x/y grid boundaries get their class correction taps in-kernel (no fix-up)
+    ClsTab cls;
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
 
@@ -88,7 +90,7 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 // MODE 1: rc = R (b - A xi)
 // MODE 2: y = xi + R^T e ; xo = y + omega (b - A y)/d
 // MODE 3: xo = omega b/diag (first Jacobi sweep from x = 0) ; rc = R (b - A xo)      [xi == b]
-template <int MODE, int NT>
+template <int MODE, int NT, bool CLS>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);
@@ -263,6 +265,25 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
             double ax1 = P.d * va.y + P.c1 * (va.x + ra) + P.cS * (vn.y + vb.y) + P.cP * (ma.y + pa.y);
             double ax2 = P.d * vb.x + P.c1 * (lb + vb.y) + P.cS * (va.x + vs.x) + P.cP * (mb.x + pb.x);
             double ax3 = P.d * vb.y + P.c1 * (vb.x + rb) + P.cS * (va.y + vs.y) + P.cP * (mb.y + pb.y);
+            if (CLS) {
+                // positional stencil classes: elements on the x/y grid boundaries add their correction taps
+                const int ya = y0 + 2 * py[k];
+                const int cya = (ya == 0) ? 0 : 3, cyb = (ya + 1 == P.NYg - 1) ? 6 : 3;      // 3*cy
+                const int cxx = (px[k] == 0) ? 0 : 1, cxy = (px[k] == HX - 1) ? 2 : 1;       // cx of .x / .y
+                auto corr = [&](int cls, int o) {
+                    double a = 0.0;
+                    for (int t = 0; t < P.cls.ntap[cls]; ++t) {
+                        const int dz = P.cls.dz[cls][t];
+                        const double *pl = dz == 0 ? sc : (dz > 0 ? sp : sm);
+                        a += P.cls.coef[cls][t] * pl[o + P.cls.soff[cls][t]];
+                    }
+                    return a;
+                };
+                if (cya + cxx != 4) ax0 += corr(cya + cxx, oa);
+                if (cya + cxy != 4) ax1 += corr(cya + cxy, oa + 1);
+                if (cyb + cxx != 4) ax2 += corr(cyb + cxx, ob);
+                if (cyb + cxy != 4) ax3 += corr(cyb + cxy, ob + 1);
+            }
             const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
             if (MODE == 1 || MODE == 3) {
                 double a = acc[k];
@@ -956,6 +977,11 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->ZL = ZL;
     P->has_exc = 0;
     P->colour = -1;
+    P->use_cls = 0;
+    if (L.kind == OMG_KIND_BAND_EXC && L.classed && XH == 0) {
+        P->use_cls = 1;
+        P->cls = L.cls;
+    }
     return true;
 }
 
@@ -963,16 +989,16 @@ static size_t st3_smem(const St3 &P) { return (size_t)P.NS * P.SPAN * sizeof(dou
 
 template <int MODE, int NT, bool SPLIT>
 static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
-    static bool attr_set = false;
+    static bool attr_set[2] = {false, false};
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
-    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256> : k_st3<MODE, NT>;
-    if (!attr_set) {
+    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256> : (P.use_cls ? k_st3<MODE, NT, true> : k_st3<MODE, NT, false>);
+    if (!attr_set[P.use_cls ? 1 : 0]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_set = true;
+        attr_set[P.use_cls ? 1 : 0] = true;
     }
     const int chunks = (P.NYg / P.TY) * P.XC;
     const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes
@@ -1165,7 +1191,7 @@ bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *
     P.xo = xo;
     P.wod = omega / P.d;
     if (!st3_launch<0>(h, P, NT)) return false;
-    fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
+    if (!P.use_cls) fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
     return true;
 }
 
@@ -1192,7 +1218,7 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
     P.rc = rcv + L.piece_row0;
     P.w = L.Rw;
     if (!st3_launch<1>(h, P, NT)) return false;
-    fix_crows(L, x, b, rcv);
+    if (!P.use_cls) fix_crows(L, x, b, rcv);
     return true;
 }
 
@@ -1226,7 +1252,7 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
     P.w = L.Rw;
     P.wod = omega / P.d;
     if (!st3_launch<2>(h, P, NT)) return false;
-    fix_rows(L, &C, 2, xi, e, b, xo, omega);
+    if (!P.use_cls) fix_rows(L, &C, 2, xi, e, b, xo, omega);
     return true;
 }
 
@@ -1268,7 +1294,7 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
     }
     if (!st3_launch<3>(h, P, NT)) return false;
     // fix-up: x_j = omega b_j / d is recomputed from b when the diagonal is uniform (x's halos are not filled yet)
-    fix_crows(L, xo, b, rcv, L.exc_diag_uniform ? P.wod : 0.0);
+    if (!P.use_cls) fix_crows(L, xo, b, rcv, L.exc_diag_uniform ? P.wod : 0.0);
     return true;
 }
 
@@ -1300,7 +1326,7 @@ bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *
     P.wod = 1.0 / P.d;
     P.colour = colour;
     if (!st3_launch<0>(h, P, NT)) return false;
-    fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
+    if (!P.use_cls) fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
     return true;
 }
 
@@ -1336,6 +1362,6 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
     P.wod = 1.0 / P.d;
     P.colour = colour;
     if (!st3_launch<2>(h, P, NT)) return false;
-    fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
+    if (!P.use_cls) fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
     return true;
 }
