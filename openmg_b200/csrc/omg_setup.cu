@@ -794,7 +794,7 @@ static int detect_classes(omg_hierarchy *h, Level &L) {
                 int o = kv.first;
                 int dz = o > S2 / 2 ? 1 : (o < -S2 / 2 ? -1 : 0);
                 int so = o - dz * S2;
-                if (so < -(S1 + 1) || so > S1 + 1) return OMG_OK;  // outside the staged +-1 rows
+                if (so < -S1 || so > S1) return OMG_OK;          // outside the staged +-1 rows
                 if (cf.ntap[cls] >= OMG_CLS_TAPS) return OMG_OK;
                 cf.off[cls][cf.ntap[cls]] = o;
                 cf.coef[cls][cf.ntap[cls]] = kv.second;
