@@ -104,7 +104,16 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
             h->launches++;
         }
     } else if (smoother == OMG_SMOOTH_RBGS) {
-        for (int s = 0; s < sweeps; ++s)
+        for (int s = 0; s < sweeps; ++s) {
+            if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_rb_sweep(h, L, nullptr, nullptr, nullptr)) {
+                // both colours in one pass (unsharded pure-band levels)
+                ProfScope ps(h, "rbgs_sweep", lvl(h, L), 24.0 * n);
+                double *out = other(L, cur);
+                stencil_rb_sweep(h, L, cur, b, out);
+                cur = out;
+                h->launches++;
+                continue;
+            }
             for (int c = 0; c < 2; ++c) {
                 dist_halo_exchange(h, L, cur);
                 ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n);
@@ -117,6 +126,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 cur = out;
                 h->launches++;
             }
+        }
     } else {   // lexicographic GS, in place (sequential: single GPU / replicated levels only)
         dist_halo_wait(h);
         if (sweeps > 0) {
@@ -180,6 +190,17 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
         {
             ProfScope ps(h, "prolong_jacobi", l, 24.0 * L.nloc + 8.0 * L.piece_n);
             stencil_prolong_jacobi(h, L, C, cur, e, b, out, omega);
+        }
+        h->launches++;
+        return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+    }
+    if (sweeps > 0 && smoother == OMG_SMOOTH_RBGS && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_prolong_rb_sweep(h, L, C, nullptr, nullptr, nullptr, nullptr)) {          // applicability probe
+        // correction fused with the whole first post-smoothing sweep
+        double *out = other(L, cur);
+        {
+            ProfScope ps(h, "prolong_rbgs_sweep", l, 24.0 * L.nloc + 8.0 * L.piece_n);
+            stencil_prolong_rb_sweep(h, L, C, cur, e, b, out);
         }
         h->launches++;
         return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);

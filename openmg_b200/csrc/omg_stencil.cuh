@@ -18,3 +18,7 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
 bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *xi, const double *b, double *xo);
 bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colour, const double *xi,
                                   const double *e, const double *b, double *xo);
+// one full two-colour sweep (colour 0 then 1) in a single pass over x; with R^T e added first.  xi == nullptr: probe
+bool stencil_rb_sweep(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo);
+bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
+                              const double *b, double *xo);
