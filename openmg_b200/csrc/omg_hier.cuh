@@ -46,6 +46,9 @@ struct Level {
     bool exc_diag_uniform = true; // every exception row has a_ii == band.diag
     bool classed = false;         // all exception rows follow the 9 positional stencil classes below
     ClsTab cls{};
+    bool classed2 = false;        // 2-D analogue: rows of the first / last grid column carry three correction taps each
+    double c2l[3] = {0, 0, 0};    // first column: deltas of the taps -1, -(N+1), +(N-1)
+    double c2r[3] = {0, 0, 0};    // last column:  deltas of the taps +1, +(N+1), -(N-1)
     // full CSR (sorted columns, global indices == local on one GPU); may be absent for a band level 0
     int64_t nnz = 0;
     int *ptr = nullptr, *col = nullptr;

@@ -823,6 +823,67 @@ static int detect_classes(omg_hierarchy *h, Level &L) {
     return OMG_OK;
 }
 
+// 2-D Galerkin levels: the rows of the first and of the last grid column deviate from the band by three taps each
+// (offsets -1, -(N+1), +(N-1) resp. +1, +(N+1), -(N-1)); everything else is the truncated band.
+static int detect_classes2(omg_hierarchy *h, Level &L) {
+    L.classed2 = false;
+    if (L.kind != OMG_KIND_BAND_EXC || L.band.nb != 6 || !L.ptr || getenv("OMG_NO_CLASSES")) return OMG_OK;
+    const BandOp &B = L.band;
+    int N = B.off[4];
+    if (B.off[2] != -1 || B.off[3] != 1 || B.off[5] != N + 1 || B.off[1] != -N || B.off[0] != -(N + 1)) return OMG_OK;
+    if (N < 8 || L.n % N != 0 || L.n / N < 4) return OMG_OK;
+    int NY = L.n / N;
+    const int allowed[2][3] = {{-1, -(N + 1), N - 1}, {1, N + 1, -(N - 1)}};
+    double dl[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    for (int side = 0; side < 2; ++side) {
+        int r = (NY / 2) * N + (side ? N - 1 : 0);
+        int hp[2];
+        CUDA_TRY(cudaMemcpy(hp, L.ptr + r, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        int len = hp[1] - hp[0];
+        if (len <= 0 || len > 32) return OMG_OK;
+        std::vector<int> hc(len);
+        std::vector<double> hv(len);
+        CUDA_TRY(cudaMemcpy(hc.data(), L.col + hp[0], len * sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(hv.data(), L.val + hp[0], len * sizeof(double), cudaMemcpyDeviceToHost));
+        std::map<int, double> delta;
+        for (int t = 0; t < len; ++t) delta[hc[t] - r] += hv[t];
+        delta[0] -= B.diag;
+        for (int k = 0; k < B.nb; ++k) delta[B.off[k]] -= B.coef[k];
+        for (auto &kv : delta) {
+            if (kv.second == 0.0) continue;
+            int t = 0;
+            while (t < 3 && allowed[side][t] != kv.first) ++t;
+            if (t == 3) return OMG_OK;
+            dl[side][t] = kv.second;
+        }
+    }
+    ClsFlat cf{};
+    for (int cy = 0; cy < 3; ++cy)
+        for (int side = 0; side < 2; ++side) {
+            int cls = 3 * cy + (side ? 2 : 0);
+            for (int t = 0; t < 3; ++t)
+                if (dl[side][t] != 0.0) {
+                    cf.off[cls][cf.ntap[cls]] = allowed[side][t];
+                    cf.coef[cls][cf.ntap[cls]] = dl[side][t];
+                    cf.ntap[cls]++;
+                }
+        }
+    int *bad = nullptr, hb = 0;
+    OMG_TRY(h_alloc_t(h, &bad, 1, true));
+    k_check_classes<<<cdiv(L.n, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.ptr, L.col, L.val, L.exc_mask, L.n, B, cf, N, NY, bad);
+    CUDA_TRY(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaGetLastError());
+    h_free(h, bad);
+    if (hb) return OMG_OK;
+    for (int t = 0; t < 3; ++t) {
+        L.c2l[t] = dl[0][t];
+        L.c2r[t] = dl[1][t];
+    }
+    L.classed2 = true;
+    return OMG_OK;
+}
+
 static int detect_band(omg_hierarchy *h, Level &L) {
     L.kind = OMG_KIND_CSR;
     if (h->flags & OMG_FLAG_FORCE_CSR) return OMG_OK;
@@ -941,6 +1002,7 @@ static int detect_band(omg_hierarchy *h, Level &L) {
         h_free(h, cmask);
         h_free(h, cpre);
     }
+    if (L.band.nb == 6 && L.band.off[5] == L.band.off[4] + 1) return detect_classes2(h, L);
     return detect_classes(h, L);
 }
 
@@ -1334,7 +1396,7 @@ static int alloc_vectors(omg_hierarchy *h) {
                     reach2[l] = a;
             }
         L.pad = (2 * reach[l] + 15) / 16 * 16;    // the 2.5-D stencil path stages plane -1 with its halo rows
-        if (L.kind != OMG_KIND_CSR && L.band.nb == 2 && L.n >= 512) L.pad = std::max(L.pad, 2048 + 16);   // 1-D rows view
+        if (L.kind != OMG_KIND_CSR && L.band.nb == 2 && L.n >= 512) L.pad = std::max(L.pad, 2 * 2048 + 16);   // 1-D rows view (two rows: fused two-colour sweep)
     }
     // ---- slab partition (multi-GPU): row0 / nloc per level
     std::vector<int64_t> lead(nlev), rows(nlev), row0(nlev), nloc(nlev);

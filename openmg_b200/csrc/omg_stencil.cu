@@ -627,10 +627,12 @@ struct St2 {
     int yg0, NYg;          // global index of local row 0, global rows
     int colour, cflat;     // -1: all rows; else the colour relaxed; cflat: colour = x & 1, else (x + y) & 1
     int oned;              // 1-D problem viewed as rows of N: restriction pairs x only, coarse row length N/2 per row
+    int use_cls;           // rows of the first / last grid column get their correction taps in-kernel (no fix-up)
+    double c2l[3], c2r[3]; // deltas of the taps -1, -(N+1), +(N-1)  /  +1, +(N+1), -(N-1)
     double d, c1, cN, cD, wod, w;
 };
 
-template <int MODE>
+template <int MODE, bool CLS>
 __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);
@@ -749,6 +751,10 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
             double l = sc[o - 1], r = sc[o + 2], ml = sm[o - 1], pr = sp[o + 2];
             double ax0 = P.d * c.x + P.c1 * (l + c.y) + P.cN * (m.x + p.x) + P.cD * (ml + p.y);
             double ax1 = P.d * c.y + P.c1 * (c.x + r) + P.cN * (m.y + p.y) + P.cD * (m.x + pr);
+            if (CLS) {
+                if (x0 + 2 * pi == 0) ax0 += P.c2l[0] * l + P.c2l[1] * ml + P.c2l[2] * sp[o - 1];
+                if (x0 + 2 * pi == P.N - 2) ax1 += P.c2r[0] * r + P.c2r[1] * pr + P.c2r[2] * sm[o + 2];
+            }
             const long long gi = (long long)y * P.N + x0 + 2 * pi;
             if (MODE == 1 || MODE == 3) {
                 double a = acc[k];
@@ -800,11 +806,12 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
 // one halo row per segment end (recomputed, bit-identical to the owner's values); raw rows carry 4 halo columns.
 // Points outside the global vector stay zero (the pads), as in the reference's truncated band.
 // MODE 0: x = xi.   MODE 2: x = xi + R^T e (raw rows transformed in shared memory when they land).
-// Pure-band levels only: exception rows of colour c0 would have to be repaired between the two passes.
+// Levels with exception rows qualify only when the kernel corrects them itself (CLS: the first / last grid column
+// of 2-D Galerkin levels): a fix-up kernel would have to run between the two passes.
 #define ST2RB_PP 5         // pairs per thread per row, halo pairs included
 #define ST2RB_TPT 5        // staged raw pairs per thread in the transform
 
-template <int MODE>
+template <int MODE, bool CLS>
 __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NT = ST2_NT;
@@ -816,8 +823,10 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
     const int x0 = (int)blockIdx.x * P.XW;
     const int y0 = (int)blockIdx.y * P.YL;
     const int y1 = min(y0 + P.YL, P.NY);
-    const int rlo = max(y0 - 2, -1), rhi = min(y1 + 1, P.NY);       // staged raw rows
-    const int first = max(y0 - 1, 0);                               // first row pass A runs on
+    // Pass A also runs on the row slots -1 and NY: their wrapped halo pairs are the first / last pair of the
+    // vector, which the column-correction taps +-(N-1) of the corner rows read.  Everything else there is pad.
+    const int rlo = y0 - 2, rhi = y1 + 1;                           // staged raw rows
+    const int first = y0 - 1;                                       // first row pass A runs on
     const long long ntot = (long long)P.NY * P.N;
     const uint32_t row_bytes = (uint32_t)RP * 8u;
     const int c0 = P.colour;
@@ -881,9 +890,8 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
 
     // (fetching b / e one row ahead in registers was measured and was slower: 0.38 vs 0.34 ms on 8192^2)
     for (int it = y0 - 1; it <= y1; ++it) {
-        const bool actA = (it >= 0 && it < P.NY);
         double *mw = mid_row(it);
-        if (actA) {
+        {
             double2 bv[ST2RB_PP];
 #pragma unroll
             for (int k = 0; k < ST2RB_PP; ++k) {
@@ -917,20 +925,18 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
                     double2 m = lds2(sm + o), q = lds2(sp + o);
                     if (ex) {
                         double ax0 = P.d * c.x + P.c1 * (sc[o - 1] + c.y) + P.cN * (m.x + q.x) + P.cD * (sm[o - 1] + q.y);
+                        if (CLS && (xg == 0 || xg == P.N))         // first grid column (also as the wrapped right halo pair)
+                            ax0 += P.c2l[0] * sc[o - 1] + P.c2l[1] * sm[o - 1] + P.c2l[2] * sp[o - 1];
                         c.x += P.wod * (bv[k].x - ax0);
                     } else {
                         double ax1 = P.d * c.y + P.c1 * (c.x + sc[o + 2]) + P.cN * (m.y + q.y) + P.cD * (m.x + sp[o + 2]);
+                        if (CLS && (xg == P.N - 2 || xg == -2))    // last grid column (also as the wrapped left halo pair)
+                            ax1 += P.c2r[0] * sc[o + 2] + P.c2r[1] * sp[o + 2] + P.c2r[2] * sm[o + 2];
                         c.y += P.wod * (bv[k].y - ax1);
                     }
                 }
                 bnew[k] = ex ? bv[k].y : bv[k].x;
                 sts2(mw + 2 * p, c);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < ST2RB_PP; ++k) {
-                int p = tid + k * NT;
-                if (p < NPA) sts2(mw + 2 * p, make_double2(0.0, 0.0));
             }
         }
         __syncthreads();        // mid row `it` complete
@@ -944,11 +950,14 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
                 if (p < 1 || p > HXW) continue;
                 const int o = 2 * p;
                 double2 c = lds2(sc + o), m = lds2(sm + o), q = lds2(sp + o);
+                const int xg = x0 - 2 + 2 * p;
                 if (ex) {       // the odd element has the second colour
                     double ax1 = P.d * c.y + P.c1 * (c.x + sc[o + 2]) + P.cN * (m.y + q.y) + P.cD * (m.x + sp[o + 2]);
+                    if (CLS && xg == P.N - 2) ax1 += P.c2r[0] * sc[o + 2] + P.c2r[1] * sp[o + 2] + P.c2r[2] * sm[o + 2];
                     c.y += P.wod * (bold[k] - ax1);
                 } else {
                     double ax0 = P.d * c.x + P.c1 * (sc[o - 1] + c.y) + P.cN * (m.x + q.x) + P.cD * (sm[o - 1] + q.y);
+                    if (CLS && xg == 0) ax0 += P.c2l[0] * sc[o - 1] + P.c2l[1] * sm[o - 1] + P.c2l[2] * sp[o - 1];
                     c.x += P.wod * (bold[k] - ax0);
                 }
                 *reinterpret_cast<double2 *>(P.xo + (long long)r * P.N + x0 + 2 * (p - 1)) = c;
@@ -957,7 +966,7 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
 #pragma unroll
         for (int k = 0; k < ST2RB_PP; ++k) bold[k] = bnew[k];
         __syncthreads();        // raw row it-1 and mid row it-2 are free
-        if (tid == 0 && actA) {
+        if (tid == 0) {
             int rn = it - 1 + NS;
             if (rn <= rhi) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1288,6 +1297,7 @@ static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
             break;
         }
     if (XW == 0) return false;
+    if (rb && L.pad < 2 * N + 4) return false;        // the fused sweep stages the row slots -2 and NY+1
     if (!rb && (XW + 4) / 2 > ST2_NT * ST2_TPT) return false;
     if (rb && (XW + 8) / 2 > ST2_NT * ST2RB_TPT) return false;
     P->N = N;
@@ -1310,6 +1320,14 @@ static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
     P->cD = cD;
     P->colour = -1;
     P->cflat = L.colour.flat;
+    P->use_cls = 0;
+    if (L.kind == OMG_KIND_BAND_EXC && L.classed2 && !oned && B.nb == 6) {
+        P->use_cls = 1;
+        for (int t = 0; t < 3; ++t) {
+            P->c2l[t] = L.c2l[t];
+            P->c2r[t] = L.c2r[t];
+        }
+    }
     {   // y-segments: same trade-off as the z-segments of the 3-D kernel
         int slots = 2 * std::max(g.sm_count, 1);
         int YL = NY;
@@ -1321,7 +1339,7 @@ static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
             long long ctas = (long long)P->XC * ns;
             long long waves = (ctas + slots - 1) / slots;
             if (waves > 6) break;
-            double eff = (yl / (yl + (rb ? 4.5 : 2.5))) * ((double)ctas / (double)(waves * slots));
+            double eff = (yl / (yl + (rb ? 4.5 : 2.5))) * ((double)ctas / (double)(waves * slots));   // rows staged beyond the segment
             if (eff > best + 1e-9) {
                 best = eff;
                 YL = yl;
@@ -1334,17 +1352,18 @@ static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
 
 template <int MODE>
 static bool st2_launch(omg_hierarchy *h, const St2 &P) {
-    static bool attr_set = false;
+    static bool attr_set[2] = {false, false};
     size_t smem = (size_t)P.NS * P.PITCH * sizeof(double) + 8 * sizeof(uint64_t);
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_st2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    void (*kern)(const St2) = P.use_cls ? k_st2<MODE, true> : k_st2<MODE, false>;
+    if (!attr_set[P.use_cls ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_set = true;
+        attr_set[P.use_cls ? 1 : 0] = true;
     }
     dist_halo_wait(h);
-    k_st2<MODE><<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
+    kern<<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
     return true;
 }
 
@@ -1355,23 +1374,25 @@ static bool colour2_ok(const Level &L, const St2 &P) {
 // fused two-colour sweep (k_st2rb): pure-band, unsharded levels
 static bool st2rb_params(Level &L, St2 *P, bool need_regular) {
     static const bool off = getenv("OMG_NO_RBFUSE") != nullptr;
-    if (off || L.kind != OMG_KIND_BAND || L.slab) return false;
-    return st2_params(L, P, need_regular, true) && colour2_ok(L, *P);
+    if (off || L.kind == OMG_KIND_CSR || L.slab) return false;
+    if (!st2_params(L, P, need_regular, true) || !colour2_ok(L, *P)) return false;
+    return L.kind == OMG_KIND_BAND || P->use_cls;     // exception rows only if the kernel corrects them itself
 }
 
 template <int MODE>
 static bool st2rb_launch(omg_hierarchy *h, const St2 &P) {
-    static bool attr_set = false;
+    static bool attr_set[2] = {false, false};
     size_t smem = ((size_t)P.NS * (P.XW + 8) + (size_t)3 * (P.XW + 4)) * sizeof(double) + 8 * sizeof(uint64_t);
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_st2rb<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    void (*kern)(const St2) = P.use_cls ? k_st2rb<MODE, true> : k_st2rb<MODE, false>;
+    if (!attr_set[P.use_cls ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_set = true;
+        attr_set[P.use_cls ? 1 : 0] = true;
     }
     dist_halo_wait(h);
-    k_st2rb<MODE><<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
+    kern<<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
     return true;
 }
 
@@ -1386,7 +1407,7 @@ bool stencil_jacobi(omg_hierarchy *h, Level &L, const double *xi, const double *
         Q.xo = xo;
         Q.wod = omega / Q.d;
         if (!st2_launch<0>(h, Q)) return false;
-        fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
+        if (!Q.use_cls) fix_rows(L, nullptr, 0, xi, nullptr, b, xo, omega);
         return true;
     }
     if (!st3_params(L, &P, &NT, false)) return false;
@@ -1413,7 +1434,7 @@ bool stencil_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const doubl
         Q.rc = rcv + L.piece_row0;
         Q.w = L.Rw;
         if (!st2_launch<1>(h, Q)) return false;
-        fix_crows(L, x, b, rcv);
+        if (!Q.use_cls) fix_crows(L, x, b, rcv);
         return true;
     }
     if (!st3_params(L, &P, &NT, false) || !regular_matches(L, P)) return false;
@@ -1443,7 +1464,7 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
         Q.w = L.Rw;
         Q.wod = omega / Q.d;
         if (!st2_launch<2>(h, Q)) return false;
-        fix_rows(L, &C, 2, xi, e, b, xo, omega);
+        if (!Q.use_cls) fix_rows(L, &C, 2, xi, e, b, xo, omega);
         return true;
     }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
@@ -1479,7 +1500,7 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         Q.w = L.Rw;
         Q.wod = omega / Q.d;
         if (!st2_launch<3>(h, Q)) return false;
-        fix_crows(L, xo, b, rcv, Q.wod);
+        if (!Q.use_cls) fix_crows(L, xo, b, rcv, Q.wod);
         return true;
     }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P)) return false;
@@ -1520,7 +1541,7 @@ bool stencil_colour_relax(omg_hierarchy *h, Level &L, int colour, const double *
         Q.wod = 1.0 / Q.d;
         Q.colour = colour;
         if (!st2_launch<0>(h, Q)) return false;
-        fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
+        if (!Q.use_cls) fix_rows(L, nullptr, 0, xi, nullptr, b, xo, 1.0, colour);
         return true;
     }
     if (!st3_params(L, &P, &NT, false) || !grid_colour_matches(L, P)) return false;
@@ -1552,7 +1573,7 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
         Q.wod = 1.0 / Q.d;
         Q.colour = colour;
         if (!st2_launch<2>(h, Q)) return false;
-        fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
+        if (!Q.use_cls) fix_rows(L, &C, 2, xi, e, b, xo, 1.0, colour);
         return true;
     }
     if (!st3_params(L, &P, &NT, true) || !regular_matches(L, P) || !grid_colour_matches(L, P)) return false;

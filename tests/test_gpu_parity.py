@@ -169,7 +169,7 @@ def test_kernels_vs_oracle(case, flags):
 
 # shapes on which the structured (TMA-staged) kernels apply: many y-segments, several x-chunks, flat-index wraps
 @pytest.mark.parametrize("shape,gl", [((256, 256), 2), ((1 << 15,), 3), ((1024, 1024), 3), ((4096, 4096), 1)])
-def test_structured_two_colour_sweep_vs_oracle(shape, gl):
+def test_structured_kernels_vs_oracle(shape, gl):
     s1 = len(shape) == 1
     A0 = orc.poisson_csr(shape, sparse_1d=s1)
     big = A0.shape[0] > (1 << 21)
@@ -193,6 +193,11 @@ def test_structured_two_colour_sweep_vs_oracle(shape, gl):
         for sweeps in (1, 2):
             close(h.prolong_correct_smooth(l, b, e, x, sweeps, "rbgs"), orc.rbgs(Al, b, y.copy(), sweeps, col),
                   RB_RTOL, "prolong+rbgs %d sweeps L%d" % (sweeps, l))
+        # the Jacobi-side structured kernels on the same levels (coarse 2-D levels: in-kernel column corrections)
+        close(h.smooth(l, b, x, 2, "jacobi", 0.8), orc.jacobi(Al, b, x.copy(), 2, 0.8), JAC_RTOL, "jacobi L%d" % l)
+        close(h.residual_restrict(l, b, x), R[l].dot(b - Al.dot(x)), 1e-13, "residual_restrict L%d" % l)
+        close(h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8), orc.jacobi(Al, b, y.copy(), 1, 0.8),
+              JAC_RTOL, "prolong+jacobi L%d" % l)
     h.close()
 
 
