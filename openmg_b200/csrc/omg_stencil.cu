@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2(const St2 P) {
 #define ST2RB_PP 5         // pairs per thread per row, halo pairs included
 #define ST2RB_TPT 5        // staged raw pairs per thread in the transform
 
-template <int MODE, bool CLS>
+template <int MODE, bool CLS, bool HASN>
 __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NT = ST2_NT;
@@ -855,6 +855,7 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
     const int HXW = P.XW >> 1;
     const int NPA = HXW + 2;         // pass-A pairs: pair p covers columns x0 - 2 + 2p, +1
     const int HRP = RP >> 1;
+    const int MPH = MP >> 1;         // pairs per mid row
 
     double bold[ST2RB_PP], bnew[ST2RB_PP];      // b of the element pass B relaxes: row it-1 / row it
 #pragma unroll
@@ -922,42 +923,62 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
                 const int flip = (xg < 0 || xg >= P.N) ? 1 : 0;
                 const bool ex = P.cflat ? (c0 == 0) : (((it + flip) & 1) == c0);
                 if (gi >= 0 && gi < ntot) {
-                    double2 m = lds2(sm + o), q = lds2(sp + o);
+                    // only the taps with a non-zero coefficient are read (level 0 has no +-N pair: HASN = false)
                     if (ex) {
-                        double ax0 = P.d * c.x + P.c1 * (sc[o - 1] + c.y) + P.cN * (m.x + q.x) + P.cD * (sm[o - 1] + q.y);
+                        const double l = sc[o - 1], ml = sm[o - 1];
+                        double ax0 = P.d * c.x + P.c1 * (l + c.y);
+                        if (HASN) {
+                            double2 q = lds2(sp + o);
+                            ax0 += P.cN * (sm[o] + q.x) + P.cD * (ml + q.y);
+                        } else {
+                            ax0 += P.cD * (ml + sp[o + 1]);
+                        }
                         if (CLS && (xg == 0 || xg == P.N))         // first grid column (also as the wrapped right halo pair)
-                            ax0 += P.c2l[0] * sc[o - 1] + P.c2l[1] * sm[o - 1] + P.c2l[2] * sp[o - 1];
+                            ax0 += P.c2l[0] * l + P.c2l[1] * ml + P.c2l[2] * sp[o - 1];
                         c.x += P.wod * (bv[k].x - ax0);
                     } else {
-                        double ax1 = P.d * c.y + P.c1 * (c.x + sc[o + 2]) + P.cN * (m.y + q.y) + P.cD * (m.x + sp[o + 2]);
+                        const double r = sc[o + 2], pr = sp[o + 2];
+                        double ax1 = P.d * c.y + P.c1 * (c.x + r);
+                        if (HASN) {
+                            double2 m = lds2(sm + o);
+                            ax1 += P.cN * (m.y + sp[o + 1]) + P.cD * (m.x + pr);
+                        } else {
+                            ax1 += P.cD * (sm[o] + pr);
+                        }
                         if (CLS && (xg == P.N - 2 || xg == -2))    // last grid column (also as the wrapped left halo pair)
-                            ax1 += P.c2r[0] * sc[o + 2] + P.c2r[1] * sp[o + 2] + P.c2r[2] * sm[o + 2];
+                            ax1 += P.c2r[0] * r + P.c2r[1] * pr + P.c2r[2] * sm[o + 2];
                         c.y += P.wod * (bv[k].y - ax1);
                     }
                 }
                 bnew[k] = ex ? bv[k].y : bv[k].x;
-                sts2(mw + 2 * p, c);
+                // mid rows are stored de-interleaved (even elements, then odd elements): pass B reads them conflict-free
+                mw[p] = c.x;
+                mw[MPH + p] = c.y;
             }
         }
         __syncthreads();        // mid row `it` complete
         const int r = it - 1;
         if (r >= y0) {
-            const double *sm = mid_row(r - 1), *sc = mid_row(r), *sp = mid_row(r + 1);
+            const double *em = mid_row(r - 1), *ec = mid_row(r), *ep = mid_row(r + 1);     // even elements of the pairs
+            const double *om = em + MPH, *oc = ec + MPH, *op = ep + MPH;                   // odd elements
             const bool ex = P.cflat ? (c0 == 0) : ((r & 1) == c0);
 #pragma unroll
             for (int k = 0; k < ST2RB_PP; ++k) {
                 int p = tid + k * NT;
                 if (p < 1 || p > HXW) continue;
-                const int o = 2 * p;
-                double2 c = lds2(sc + o), m = lds2(sm + o), q = lds2(sp + o);
+                double2 c = make_double2(ec[p], oc[p]);
                 const int xg = x0 - 2 + 2 * p;
                 if (ex) {       // the odd element has the second colour
-                    double ax1 = P.d * c.y + P.c1 * (c.x + sc[o + 2]) + P.cN * (m.y + q.y) + P.cD * (m.x + sp[o + 2]);
-                    if (CLS && xg == P.N - 2) ax1 += P.c2r[0] * sc[o + 2] + P.c2r[1] * sp[o + 2] + P.c2r[2] * sm[o + 2];
+                    const double rr = ec[p + 1], pr = ep[p + 1];
+                    double ax1 = P.d * c.y + P.c1 * (c.x + rr) + P.cD * (em[p] + pr);
+                    if (HASN) ax1 += P.cN * (om[p] + op[p]);
+                    if (CLS && xg == P.N - 2) ax1 += P.c2r[0] * rr + P.c2r[1] * pr + P.c2r[2] * em[p + 1];
                     c.y += P.wod * (bold[k] - ax1);
                 } else {
-                    double ax0 = P.d * c.x + P.c1 * (sc[o - 1] + c.y) + P.cN * (m.x + q.x) + P.cD * (sm[o - 1] + q.y);
-                    if (CLS && xg == 0) ax0 += P.c2l[0] * sc[o - 1] + P.c2l[1] * sm[o - 1] + P.c2l[2] * sp[o - 1];
+                    const double l = oc[p - 1], ml = om[p - 1];
+                    double ax0 = P.d * c.x + P.c1 * (l + c.y) + P.cD * (ml + op[p]);
+                    if (HASN) ax0 += P.cN * (em[p] + ep[p]);
+                    if (CLS && xg == 0) ax0 += P.c2l[0] * l + P.c2l[1] * ml + P.c2l[2] * op[p - 1];
                     c.x += P.wod * (bold[k] - ax0);
                 }
                 *reinterpret_cast<double2 *>(P.xo + (long long)r * P.N + x0 + 2 * (p - 1)) = c;
@@ -1381,15 +1402,18 @@ static bool st2rb_params(Level &L, St2 *P, bool need_regular) {
 
 template <int MODE>
 static bool st2rb_launch(omg_hierarchy *h, const St2 &P) {
-    static bool attr_set[2] = {false, false};
+    static bool attr_set[4] = {false, false, false, false};
     size_t smem = ((size_t)P.NS * (P.XW + 8) + (size_t)3 * (P.XW + 4)) * sizeof(double) + 8 * sizeof(uint64_t);
-    void (*kern)(const St2) = P.use_cls ? k_st2rb<MODE, true> : k_st2rb<MODE, false>;
-    if (!attr_set[P.use_cls ? 1 : 0]) {
+    const bool hasn = P.cN != 0.0;
+    void (*kern)(const St2) = P.use_cls ? (hasn ? k_st2rb<MODE, true, true> : k_st2rb<MODE, true, false>)
+                                        : (hasn ? k_st2rb<MODE, false, true> : k_st2rb<MODE, false, false>);
+    const int vi = (P.use_cls ? 1 : 0) + (hasn ? 2 : 0);
+    if (!attr_set[vi]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_set[P.use_cls ? 1 : 0] = true;
+        attr_set[vi] = true;
     }
     dist_halo_wait(h);
     kern<<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
