@@ -130,6 +130,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
         p = act[k] ? p : 0;
         py[k] = p / HX;
         px[k] = p - py[k] * HX;
+        if (CLS && k == 1 && (HX & 63) == 0) {
+            // the class corrections run on the lanes px == 0 and px == HX-1 only: rotate the second patch of every
+            // thread by half a row so that each warp owns one of them instead of half the warps owning two
+            px[k] += HX >> 1;
+            if (px[k] >= HX) px[k] -= HX;
+        }
     }
     double acc[ST_PPT];
 #pragma unroll
@@ -1270,7 +1276,8 @@ static void fix_crows(Level &L, const double *x, const double *b, double *rcv, d
 // ---------------------------------------------------------------- 2-D host side
 
 static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
-    if (L.kind == OMG_KIND_CSR || L.slab) return false;      // slab levels: the generic kernels (3-D has its own slab path)
+    if (L.kind == OMG_KIND_CSR) return false;
+    if (L.slab && (rb || getenv("OMG_NO_ST2_SLAB"))) return false;     // the single-pass sweep needs two halo rows
     const BandOp &B = L.band;
     int N = 0;
     double c1 = 0, cN = 0, cD = 0;
@@ -1306,6 +1313,7 @@ static bool st2_params(Level &L, St2 *P, bool need_regular, bool rb = false) {
     int NY = L.nloc / N;
     if ((!oned && (NY & 1)) || NY < 4) return false;
     if (L.pad < N + 4) return false;
+    if (L.slab && L.halo < N + 2) return false;       // rows -1 and NY (+2 halo columns) come from the neighbours
     if (need_regular && !oned && !(L.regular && L.reg.alpha == 2 && L.reg.fs2 == N)) return false;
     if (need_regular && oned && !(L.regular && L.reg.alpha == 1)) return false;
     P->oned = oned ? 1 : 0;
@@ -1386,6 +1394,14 @@ static bool st2_launch(omg_hierarchy *h, const St2 &P) {
     dist_halo_wait(h);
     kern<<<dim3(P.XC, (P.NY + P.YL - 1) / P.YL), ST2_NT, smem, g.stream>>>(P);
     return true;
+}
+
+// The 2-D kernels index the coarse vector by LOCAL coarse row (fine local row >> 1); the coarse level may be a slab
+// (its owned row 0 is that row) or replicated (global rows): rebase accordingly.
+static const double *st2_coarse_base(const Level &L, const Level &C, const St2 &Q, const double *e) {
+    (void)L;
+    long long first = (long long)(Q.oned ? Q.yg0 : (Q.yg0 >> 1)) * Q.cs;    // global coarse row*cs of local coarse row 0
+    return e - C.row0 + first;
 }
 
 static bool colour2_ok(const Level &L, const St2 &P) {
@@ -1484,7 +1500,7 @@ bool stencil_prolong_jacobi(omg_hierarchy *h, Level &L, Level &C, const double *
         Q.xi = xi;
         Q.b = b;
         Q.xo = xo;
-        Q.e = e;
+        Q.e = st2_coarse_base(L, C, Q, e);
         Q.w = L.Rw;
         Q.wod = omega / Q.d;
         if (!st2_launch<2>(h, Q)) return false;
@@ -1592,7 +1608,7 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
         Q.xi = xi;
         Q.b = b;
         Q.xo = xo;
-        Q.e = e;
+        Q.e = st2_coarse_base(L, C, Q, e);
         Q.w = L.Rw;
         Q.wod = 1.0 / Q.d;
         Q.colour = colour;

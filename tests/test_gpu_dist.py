@@ -20,7 +20,7 @@ def _ngpus():
 
 
 @pytest.mark.parametrize("shape,gl,agg", [((64, 64, 64), 3, 4096), ((128, 128, 128), 4, 1 << 16),
-                                          ((256, 256), 4, 1024), ((65536,), 8, 1024)])
+                                          ((256, 256), 4, 1024), ((1024, 1024), 5, 4096), ((65536,), 8, 1024)])
 def test_slab_sharding_matches_single_gpu(shape, gl, agg):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
