@@ -1,0 +1,162 @@
+"""CPU model of the single-pass two-colour sweep (`k_st2rb`, openmg_b200/csrc/omg_stencil.cu).
+
+The CUDA kernel relaxes colour 0 of row r from raw rows r-1..r+1 into a "mid" ring and, one row behind,
+colour 1 of row r-1 from mid rows r-2..r, per x-chunk and y-segment, with halo pairs / halo rows recomputed
+redundantly, flat-index wraps at the row ends, the first/last-column correction taps of 2-D Galerkin levels and
+pass A also run on the row slots -1 and NY.  This file restates exactly that index logic in numpy and checks it
+against the oracle's definition of the sweep (oracle.rbgs: colour 0 then colour 1, same-colour couplings lagged)
+on small hierarchies, so the *algorithm* is pinned on the CPU; the GPU parity tests pin the kernel itself.
+(The model is how the missing row slots -1 / NY were found: the +-(N-1) taps of the two corner rows read the
+first / last pair of the vector through those slots.)
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle.openmg_oracle as orc
+
+
+def band_and_classes(Al, N):
+    """Majority band {offset: coefficient} and the two column classes of a 2-D level (openmg_b200 setup logic)."""
+    n = Al.shape[0]
+    C = Al.tocoo()
+    band = {}
+    for d in np.unique(C.col - C.row):
+        vals = C.data[(C.col - C.row) == d]
+        u, c = np.unique(vals, return_counts=True)
+        if c.max() > n / 2:
+            band[int(d)] = float(u[np.argmax(c)])
+
+    def delta(r):
+        row = Al.getrow(r)
+        dl = {}
+        for c, v in zip(row.indices, row.data):
+            dl[int(c - r)] = dl.get(int(c - r), 0.0) + v
+        for k, v in band.items():
+            dl[k] = dl.get(k, 0.0) - v
+        return {k: v for k, v in dl.items() if v != 0.0}
+
+    NY = n // N
+    dL, dR = delta((NY // 2) * N), delta((NY // 2) * N + N - 1)
+    assert set(dL) <= {-1, -(N + 1), N - 1} and set(dR) <= {1, N + 1, -(N - 1)}
+    c2l = [dL.get(-1, 0.0), dL.get(-(N + 1), 0.0), dL.get(N - 1, 0.0)]
+    c2r = [dR.get(1, 0.0), dR.get(N + 1, 0.0), dR.get(-(N - 1), 0.0)]
+    return band, c2l, c2r
+
+
+def fused_sweep_model(x, b, N, band, c2l, c2r, cflat, XW, YL, c0=0):
+    """One two-colour sweep the way k_st2rb computes it (chunks of XW columns, segments of YL rows)."""
+    n = x.size
+    NY = n // N
+    d = band[0]
+    c1, cN, cD = band.get(1, 0.0), band.get(N, 0.0), band.get(N + 1, 0.0)
+    wod = 1.0 / d
+    PAD = 2 * N + 16
+    xp = np.zeros(n + 2 * PAD)
+    xp[PAD:PAD + n] = x
+    bp = np.zeros(n + 2 * PAD)
+    bp[PAD:PAD + n] = b
+    out = np.full(n, np.nan)
+    HXW, NPA = XW // 2, XW // 2 + 2
+    for x0 in range(0, N, XW):
+        for y0 in range(0, NY, YL):
+            y1 = min(y0 + YL, NY)
+
+            def raw(r):              # staged raw row slot r: columns x0-4 .. x0+XW+3 of the FLAT vector
+                s = PAD + r * N + x0 - 4
+                return xp[s:s + XW + 8]
+
+            mid = {}
+            for it in range(y0 - 1, y1 + 1):
+                sm, sc, sq = raw(it - 1), raw(it), raw(it + 1)
+                mw = np.zeros(XW + 4)
+                for p in range(NPA):             # pass A, halo pairs included
+                    o, xg = 2 + 2 * p, x0 - 2 + 2 * p
+                    gi = it * N + xg
+                    cx, cy = sc[o], sc[o + 1]
+                    flip = 1 if (xg < 0 or xg >= N) else 0
+                    ex = (c0 == 0) if cflat else (((it + flip) & 1) == c0)
+                    if 0 <= gi < n:
+                        if ex:
+                            ax = d * cx + c1 * (sc[o - 1] + cy) + cN * (sm[o] + sq[o]) + cD * (sm[o - 1] + sq[o + 1])
+                            if xg == 0 or xg == N:
+                                ax += c2l[0] * sc[o - 1] + c2l[1] * sm[o - 1] + c2l[2] * sq[o - 1]
+                            cx += wod * (bp[PAD + gi] - ax)
+                        else:
+                            ax = d * cy + c1 * (cx + sc[o + 2]) + cN * (sm[o + 1] + sq[o + 1]) + cD * (sm[o] + sq[o + 2])
+                            if xg == N - 2 or xg == -2:
+                                ax += c2r[0] * sc[o + 2] + c2r[1] * sq[o + 2] + c2r[2] * sm[o + 2]
+                            cy += wod * (bp[PAD + gi + 1] - ax)
+                    mw[2 * p], mw[2 * p + 1] = cx, cy
+                mid[it] = mw
+                r = it - 1
+                if r < y0:
+                    continue
+                sm, sc, sq = mid[r - 1], mid[r], mid[r + 1]
+                ex = (c0 == 0) if cflat else ((r & 1) == c0)
+                for p in range(1, HXW + 1):      # pass B, owned pairs
+                    o, xg = 2 * p, x0 - 2 + 2 * p
+                    cx, cy = sc[o], sc[o + 1]
+                    if ex:
+                        ax = d * cy + c1 * (cx + sc[o + 2]) + cN * (sm[o + 1] + sq[o + 1]) + cD * (sm[o] + sq[o + 2])
+                        if xg == N - 2:
+                            ax += c2r[0] * sc[o + 2] + c2r[1] * sq[o + 2] + c2r[2] * sm[o + 2]
+                        cy += wod * (b[r * N + xg + 1] - ax)
+                    else:
+                        ax = d * cx + c1 * (sc[o - 1] + cy) + cN * (sm[o] + sq[o]) + cD * (sm[o - 1] + sq[o + 1])
+                        if xg == 0:
+                            ax += c2l[0] * sc[o - 1] + c2l[1] * sm[o - 1] + c2l[2] * sq[o - 1]
+                        cx += wod * (b[r * N + xg] - ax)
+                    out[r * N + xg], out[r * N + xg + 1] = cx, cy
+    assert not np.isnan(out).any()
+    return out
+
+
+@pytest.mark.parametrize("shape,XW_div,YL", [((16, 16), 1, 16), ((32, 32), 2, 6), ((32, 32), 1, 2), ((64, 64), 4, 64)])
+def test_single_pass_sweep_equals_two_half_sweeps_2d(shape, XW_div, YL):
+    A0 = orc.poisson_csr(shape)
+    R = orc.restrictionList(shape, 2, 4)
+    A = orc.coeffecientList(A0, R)
+    rs = np.random.RandomState(3)
+    for l in range(len(A)):
+        Al = sp.csr_matrix(A[l])
+        n = Al.shape[0]
+        N = shape[0] >> l
+        if N < 8:
+            break
+        band, c2l, c2r = band_and_classes(Al, N)
+        if l == 0:
+            assert c2l == [0, 0, 0] and c2r == [0, 0, 0] and N not in band          # level 0: pure band, no +-N pair
+        x, b = rs.random_sample(n), rs.random_sample(n)
+        col = orc.colouring(shape, l, n)
+        want = orc.rbgs(Al, b, x.copy(), 1, col)
+        XW = max(N // XW_div, 4)
+        got = fused_sweep_model(x, b, N, band, c2l, c2r, cflat=(l == 0), XW=XW, YL=min(YL, n // N))
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max(), err_msg="level %d" % l)
+
+
+def test_single_pass_sweep_1d_rows_view():
+    """1-D levels run on the same kernel with the vector viewed as rows of N (flat colouring, c1 only)."""
+    shape = (256,)
+    A0 = sp.csr_matrix(orc.poisson_csr(shape, sparse_1d=True))
+    n = A0.shape[0]
+    rs = np.random.RandomState(4)
+    x, b = rs.random_sample(n), rs.random_sample(n)
+    want = orc.rbgs(A0, b, x.copy(), 1, orc.colouring(shape, 0, n))
+    band = {0: A0[1, 1], 1: A0[1, 2], -1: A0[1, 0]}
+    for N, XW, YL in ((32, 32, 8), (64, 16, 2), (16, 8, 3)):
+        got = fused_sweep_model(x, b, N, band, [0, 0, 0], [0, 0, 0], cflat=True, XW=XW, YL=YL)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max())
+
+
+def test_corner_rows_couple_through_the_wrapped_pairs():
+    """Why pass A also runs on the row slots -1 and NY: on a 2-D Galerkin level row (0, N-1) couples to (0, 0)
+    through the tap -(N-1) and row (NY-1, 0) to (NY-1, N-1) through +(N-1); in the staged layout those neighbours
+    are the wrapped halo pairs of the slots -1 and NY, so their mid values must exist."""
+    shape = (32, 32)
+    A = orc.coeffecientList(orc.poisson_csr(shape), orc.restrictionList(shape, 1, 4))
+    Al = sp.csr_matrix(A[1])
+    n, N = Al.shape[0], 16
+    assert Al[N - 1, 0] != 0.0 and Al[n - N, n - 1] != 0.0
+    band, c2l, c2r = band_and_classes(Al, N)
+    assert c2r[2] == Al[N - 1, 0] and c2l[2] == Al[n - N, n - 1]
