@@ -1632,9 +1632,326 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
     return true;
 }
 
+// ================================================================ 3-D single-pass two-colour sweep (EXPERIMENTAL)
+//
+// Same idea as k_st2rb one dimension up, marching in z over full-row chunks of TY rows.  An "item" is an x-pair of
+// one row; items cover rows y0-1 .. y0+TY (pass A: colour-0 point of the pair relaxed from raw planes p-1, p, p+1
+// into the mid plane p) of which rows y0 .. y0+TY-1 are stored (pass B, one plane behind: the colour-1 point of
+// plane p-1 from mid planes p-2, p-1, p).  Each thread keeps per item, across steps, the raw pair of plane p, one
+// raw element of plane p-1, the mid pair of plane p-1, one mid element of plane p-2 and the b element pass B needs:
+// z-neighbours and centres never come from shared memory, which only holds raw planes p, p+1 (+1 in flight; rows
+// y0-2 .. y0+TY+1) and mid planes p-1, p (rows y0-1 .. y0+TY).  The colour-1 point of plane p-1 sits at the same
+// in-pair position as the colour-0 point of plane p.  Rows outside [0,NY) are rows of the neighbouring plane in the
+// flat index (colour parity flips), points outside [0,n) stay zero, planes -2 and NZ+1 are all zero and not staged.
+// The index logic was validated against oracle.rbgs by a numpy model (tests/test_cpu_fused_sweep_model.py);
+// the kernel itself has NOT run on a GPU yet: it is only selected with OMG_RB3=1.
+#define ST3R_NS 3
+#define ST3R_IPT 4         // items per thread (max)
+
+struct St3R {
+    const double *xi;
+    const double *b;
+    const double *e;       // coarse correction (MODE 2)
+    double *xo;
+    int S1, S2, NY, NZ;    // row length, plane size, rows per plane, planes
+    int TY, ZL;            // rows per chunk, planes per z-segment
+    int cs1, cs2;          // coarse rows per plane, coarse row length
+    int c0;                // colour relaxed first
+    double d, c1, cS, cP, wod, w;
+};
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1) k_st3rb(const St3R P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NS = ST3R_NS;
+    const int S1 = P.S1, HX = S1 >> 1;
+    const int RS = (P.TY + 4) * S1, MS = (P.TY + 2) * S1;
+    double *raw = reinterpret_cast<double *>(smem_raw);
+    double *mid = raw + (size_t)NS * RS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(mid + 2 * (size_t)MS);
+    const int tid = threadIdx.x;
+    const int y0 = (int)blockIdx.x * P.TY;
+    const int z0 = (int)blockIdx.y * P.ZL;
+    const int z1 = min(z0 + P.ZL, P.NZ);
+    const long long ntot = (long long)P.S2 * P.NZ;
+    const uint32_t span_bytes = (uint32_t)RS * 8u;
+    const int plast = min(z1 + 1, P.NZ);          // last raw plane that exists (planes < -1 or > NZ are all zero)
+
+    auto slot_of = [&](int p) { return (p - (z0 - 2)) % NS; };
+    auto issue = [&](int p) {        // p in [-1, NZ]
+        int s_ = slot_of(p);
+        mbar_expect_tx(full + s_, span_bytes);
+        bulk_g2s(raw + (size_t)s_ * RS, P.xi + (long long)p * P.S2 + (long long)(y0 - 2) * S1, span_bytes, full + s_);
+    };
+    auto wait_plane = [&](int p) {
+        int k = p - (z0 - 2);
+        mbar_wait(full + (k % NS), (uint32_t)((k / NS) & 1));
+    };
+    // raw plane pl += w e[cell] on the whole staged span (rows y0-2 .. y0+TY+1; rows outside [0,NY) are rows of the
+    // neighbouring plane)
+    auto transform = [&](int pl) {
+        if constexpr (MODE == 2) {
+            double *sp_ = raw + (size_t)slot_of(pl) * RS;
+            const int npairs = (P.TY + 4) * HX;
+            for (int t = tid; t < npairs; t += NT) {
+                int rq = t / HX, jj = t - rq * HX;
+                int yy = y0 - 2 + rq, zz = pl;
+                if (yy < 0) {
+                    yy += P.NY;
+                    zz -= 1;
+                } else if (yy >= P.NY) {
+                    yy -= P.NY;
+                    zz += 1;
+                }
+                if (zz < 0 || zz >= P.NZ) continue;
+                double v = P.w * __ldg(P.e + ((long long)(zz >> 1) * P.cs1 + (yy >> 1)) * P.cs2 + jj);
+                double2 x = lds2(sp_ + rq * S1 + 2 * jj);
+                x.x += v;
+                x.y += v;
+                sts2(sp_ + rq * S1 + 2 * jj, x);
+            }
+        }
+    };
+
+    if (tid == 0) {
+        for (int s_ = 0; s_ < NS; ++s_) mbar_init(full + s_, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int p = z0 - 2; p <= z0; ++p) {
+            if (p >= -1 && p <= plast)
+                issue(p);
+            else
+                mbar_expect_tx(full + slot_of(p), 0);     // plane not staged: complete the phase so parities stay in step
+        }
+    }
+
+    // fixed item assignment
+    int roff[ST3R_IPT], moff[ST3R_IPT], yr[ST3R_IPT], par0[ST3R_IPT], xj[ST3R_IPT];
+    bool act[ST3R_IPT], own[ST3R_IPT];
+    const int nitems = (P.TY + 2) * HX;
+#pragma unroll
+    for (int k = 0; k < ST3R_IPT; ++k) {
+        int it = tid + k * NT;
+        act[k] = it < nitems;
+        it = act[k] ? it : 0;
+        int q = it / HX, j = it - q * HX;
+        yr[k] = y0 - 1 + q;
+        own[k] = act[k] && q >= 1 && q <= P.TY;
+        xj[k] = 2 * j;
+        roff[k] = (q + 1) * S1 + 2 * j;
+        moff[k] = q * S1 + 2 * j;
+        par0[k] = (yr[k] + ((yr[k] < 0 || yr[k] >= P.NY) ? 1 : 0) + P.c0) & 1;     // e(p) = (par0 + p) & 1
+    }
+    double2 rc[ST3R_IPT], mc[ST3R_IPT];
+    double rme[ST3R_IPT], mme[ST3R_IPT], bk[ST3R_IPT];
+
+    // prologue: registers of step p = z0-1
+    if (z0 - 2 >= -1) {
+        wait_plane(z0 - 2);
+        transform(z0 - 2);
+    }
+    wait_plane(z0 - 1);
+    transform(z0 - 1);
+    if (MODE == 2) __syncthreads();
+    {
+        const double *pm = raw + (size_t)slot_of(z0 - 2) * RS, *pc = raw + (size_t)slot_of(z0 - 1) * RS;
+#pragma unroll
+        for (int k = 0; k < ST3R_IPT; ++k) {
+            rc[k] = make_double2(0.0, 0.0);
+            mc[k] = make_double2(0.0, 0.0);
+            rme[k] = mme[k] = bk[k] = 0.0;
+            if (!act[k]) continue;
+            int e = (par0[k] + (z0 - 1)) & 1;
+            if (z0 - 2 >= -1) rme[k] = pm[roff[k] + e];
+            rc[k] = lds2(pc + roff[k]);
+        }
+    }
+    __syncthreads();        // plane z0-2 has been read by everyone
+    if (tid == 0 && z0 + 1 <= plast) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(z0 + 1);      // into the slot of plane z0-2
+    }
+
+    for (int p = z0 - 1; p <= z1; ++p) {
+        const bool has_next = (p + 1 <= plast);
+        double2 bb[ST3R_IPT];
+        bool valid[ST3R_IPT];
+#pragma unroll
+        for (int k = 0; k < ST3R_IPT; ++k) {
+            long long gi = (long long)p * P.S2 + (long long)yr[k] * S1 + xj[k];
+            valid[k] = act[k] && gi >= 0 && gi < ntot;
+            bb[k] = valid[k] ? ldg2(P.b + gi) : make_double2(0.0, 0.0);
+        }
+        if (has_next) {
+            wait_plane(p + 1);
+            transform(p + 1);
+            if (MODE == 2) __syncthreads();
+        }
+        const double *rawc = raw + (size_t)slot_of(p) * RS;
+        const double *rawn = raw + (size_t)slot_of(p + 1) * RS;
+        double *midw = mid + (size_t)(p & 1) * MS;
+        double2 rp[ST3R_IPT], mp[ST3R_IPT];
+        double bknew[ST3R_IPT];
+#pragma unroll
+        for (int k = 0; k < ST3R_IPT; ++k) {
+            rp[k] = make_double2(0.0, 0.0);
+            mp[k] = rc[k];
+            bknew[k] = 0.0;
+            if (!act[k]) continue;
+            const int e = (par0[k] + p) & 1;
+            const int o = roff[k];
+            if (has_next) rp[k] = lds2(rawn + o);
+            const double c = e ? rc[k].y : rc[k].x;
+            const double xl = e ? rc[k].x : rawc[o - 1];
+            const double xr = e ? rawc[o + 2] : rc[k].y;
+            const double yu = rawc[o - S1 + e], yd = rawc[o + S1 + e];
+            const double zp = e ? rp[k].y : rp[k].x;
+            const double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yu + yd) + P.cP * (rme[k] + zp);
+            const double bA = e ? bb[k].y : bb[k].x;
+            bknew[k] = e ? bb[k].x : bb[k].y;
+            if (valid[k]) {
+                const double nv = c + P.wod * (bA - ax);
+                if (e)
+                    mp[k].y = nv;
+                else
+                    mp[k].x = nv;
+            }
+            sts2(midw + moff[k], mp[k]);
+        }
+        __syncthreads();        // mid plane p complete
+        if (p - 1 >= z0) {
+            const double *midp = mid + (size_t)((p - 1) & 1) * MS;
+#pragma unroll
+            for (int k = 0; k < ST3R_IPT; ++k) {
+                if (!own[k]) continue;
+                const int e = (par0[k] + p) & 1;      // position of the colour-1 point of plane p-1
+                const int o = moff[k];
+                const double c = e ? mc[k].y : mc[k].x;
+                const double xl = e ? mc[k].x : midp[o - 1];
+                const double xr = e ? midp[o + 2] : mc[k].y;
+                const double yu = midp[o - S1 + e], yd = midp[o + S1 + e];
+                const double zp = e ? mp[k].y : mp[k].x;
+                const double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yu + yd) + P.cP * (mme[k] + zp);
+                const double nv = c + P.wod * (bk[k] - ax);
+                double2 ov = mc[k];
+                if (e)
+                    ov.y = nv;
+                else
+                    ov.x = nv;
+                *reinterpret_cast<double2 *>(P.xo + (long long)(p - 1) * P.S2 + (long long)yr[k] * S1 + xj[k]) = ov;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ST3R_IPT; ++k) {
+            const int e = (par0[k] + p) & 1;
+            mme[k] = e ? mc[k].x : mc[k].y;
+            mc[k] = mp[k];
+            rme[k] = e ? rc[k].x : rc[k].y;
+            rc[k] = rp[k];
+            bk[k] = bknew[k];
+        }
+        __syncthreads();        // raw plane p and mid plane p-1 are free
+        if (tid == 0 && p + 3 <= plast) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(p + 3);       // into the slot of plane p
+        }
+    }
+}
+
+static bool st3rb_params(Level &L, St3R *P, int *NT_out, bool need_regular) {
+    const bool on = getenv("OMG_RB3") != nullptr;       // read per call: the opt-in GPU test toggles it
+    if (!on || L.kind != OMG_KIND_BAND || L.slab || L.band.nb != 6) return false;
+    const BandOp &B = L.band;
+    if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return false;
+    if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;
+    int S1 = B.off[4], S2 = B.off[5];
+    if (S1 < 32 || (S1 & 1) || S2 % S1 != 0 || L.n % S2 != 0) return false;
+    int NY = S2 / S1, NZ = L.n / S2;
+    if ((NY & 1) || NY < 4 || NZ < 2) return false;
+    if (L.colour.flat || L.colour.alpha != 3 || L.colour.s2 != S1 || L.colour.s1 != NY) return false;
+    if (L.pad < S2 + 2 * S1) return false;        // plane -1 is staged from row y0-2
+    if (need_regular && !(L.regular && L.reg.alpha == 3 && L.reg.fs2 == S1 && L.reg.fs1 == NY)) return false;
+    const int NT = 512;
+    int TY = 0;
+    for (int t = std::min(16, NY); t >= 2; --t) {
+        if ((t & 1) || NY % t != 0) continue;
+        if ((t + 2) * (S1 / 2) > NT * ST3R_IPT) continue;
+        size_t smem = ((size_t)ST3R_NS * (t + 4) + 2 * (size_t)(t + 2)) * S1 * 8 + 64;
+        if (smem > 226 * 1024) continue;
+        TY = t;
+        break;
+    }
+    if (TY < 2) return false;
+    *NT_out = NT;
+    P->S1 = S1;
+    P->S2 = S2;
+    P->NY = NY;
+    P->NZ = NZ;
+    P->TY = TY;
+    P->cs1 = NY / 2;
+    P->cs2 = S1 / 2;
+    P->c0 = 0;
+    P->d = B.diag;
+    P->c1 = B.coef[3];
+    P->cS = B.coef[4];
+    P->cP = B.coef[5];
+    P->wod = 1.0 / B.diag;
+    {   // z-segments: 3.5 planes of overhead per segment against whole waves of one CTA per SM
+        int chunks = NY / TY, slots = std::max(g.sm_count, 1);
+        int ZL = NZ;
+        double best = -1.0;
+        for (int nseg = 1; nseg <= NZ; ++nseg) {
+            int zl = (NZ + nseg - 1) / nseg;
+            int ns = (NZ + zl - 1) / zl;
+            long long ctas = (long long)chunks * ns;
+            long long waves = (ctas + slots - 1) / slots;
+            if (waves > 16) break;
+            double eff = (zl / (zl + 3.5)) * ((double)ctas / (double)(waves * slots));
+            if (eff > best + 1e-9) {
+                best = eff;
+                ZL = zl;
+            }
+        }
+        int envZL = env_int("OMG_RB3_ZL", 0);
+        if (envZL >= 1) ZL = envZL;
+        P->ZL = std::min(std::max(ZL, 1), NZ);
+    }
+    return true;
+}
+
+template <int MODE>
+static bool st3rb_launch(omg_hierarchy *h, const St3R &P, int NT) {
+    (void)NT;
+    static bool attr_set = false;
+    size_t smem = ((size_t)ST3R_NS * (P.TY + 4) + 2 * (size_t)(P.TY + 2)) * P.S1 * sizeof(double) + 64;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_st3rb<MODE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_set = true;
+    }
+    dist_halo_wait(h);
+    k_st3rb<MODE, 512><<<dim3(P.NY / P.TY, (P.NZ + P.ZL - 1) / P.ZL), 512, smem, g.stream>>>(P);
+    return true;
+}
+
 // one full two-colour Gauss-Seidel sweep (colour 0, then colour 1) in a single pass.  xi == nullptr: probe.
 bool stencil_rb_sweep(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo) {
     St2 Q{};
+    St3R T{};
+    int NT3;
+    if (st3rb_params(L, &T, &NT3, false)) {       // experimental 3-D kernel, OMG_RB3=1 only
+        if (!xi) return true;
+        T.xi = xi;
+        T.b = b;
+        T.xo = xo;
+        return st3rb_launch<0>(h, T, NT3);
+    }
     if (!st2rb_params(L, &Q, false)) return false;
     if (!xi) return true;
     Q.xi = xi;
@@ -1650,6 +1967,17 @@ bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double
                               const double *b, double *xo) {
     (void)C;
     St2 Q{};
+    St3R T{};
+    int NT3;
+    if (st3rb_params(L, &T, &NT3, true)) {        // experimental 3-D kernel, OMG_RB3=1 only
+        if (!xi) return true;
+        T.xi = xi;
+        T.b = b;
+        T.xo = xo;
+        T.e = e;
+        T.w = L.Rw;
+        return st3rb_launch<2>(h, T, NT3);
+    }
     if (!st2rb_params(L, &Q, true)) return false;
     if (!xi) return true;
     Q.xi = xi;

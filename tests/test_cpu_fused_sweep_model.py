@@ -1,4 +1,5 @@
-"""CPU model of the single-pass two-colour sweep (`k_st2rb`, openmg_b200/csrc/omg_stencil.cu).
+"""CPU models of the single-pass two-colour sweeps (`k_st2rb` and the experimental `k_st3rb`,
+openmg_b200/csrc/omg_stencil.cu).
 
 The CUDA kernel relaxes colour 0 of row r from raw rows r-1..r+1 into a "mid" ring and, one row behind,
 colour 1 of row r-1 from mid rows r-2..r, per x-chunk and y-segment, with halo pairs / halo rows recomputed
@@ -160,3 +161,94 @@ def test_corner_rows_couple_through_the_wrapped_pairs():
     assert Al[N - 1, 0] != 0.0 and Al[n - N, n - 1] != 0.0
     band, c2l, c2r = band_and_classes(Al, N)
     assert c2r[2] == Al[N - 1, 0] and c2l[2] == Al[n - N, n - 1]
+
+
+# ------------------------------------------------------------------ 3-D: the register-pipelined variant (k_st3rb)
+
+def fused_sweep_model_3d(x, b, S1, NY, NZ, d, c1, cS, cP, TY, ZL, c0=0):
+    """One two-colour sweep the way k_st3rb computes it: full-row chunks of TY rows, z-segments of ZL planes; per
+    item (x-pair of a row) the raw pair of plane p, one raw element of plane p-1, the mid pair of plane p-1 and one
+    mid element of plane p-2 are carried from step to step ("registers"); in-plane neighbours come from the staged
+    raw plane p (pass A) resp. the stored mid plane p-1 (pass B)."""
+    S2 = S1 * NY
+    n = S2 * NZ
+    wod = 1.0 / d
+    PAD = 2 * S2
+    xp = np.zeros(n + 2 * PAD)
+    xp[PAD:PAD + n] = x
+    bp = np.zeros(n + 2 * PAD)
+    bp[PAD:PAD + n] = b
+    out = np.full(n, np.nan)
+    HX = S1 // 2
+    RS, MS = (TY + 4) * S1, (TY + 2) * S1
+    for y0 in range(0, NY, TY):
+        for z0 in range(0, NZ, ZL):
+            z1 = min(z0 + ZL, NZ)
+
+            def rawplane(p):                 # staged rows y0-2 .. y0+TY+1; planes < -1 or > NZ are all zero
+                if p < -1 or p > NZ:
+                    return None
+                s = PAD + p * S2 + (y0 - 2) * S1
+                return xp[s:s + RS]
+
+            Q, J = np.meshgrid(np.arange(TY + 2), np.arange(HX), indexing='ij')
+            Q, J = Q.ravel(), J.ravel()
+            idx = np.arange(Q.size)
+            yr = y0 - 1 + Q
+            wy = ((yr < 0) | (yr >= NY)).astype(int)       # the row belongs to the neighbouring plane: parity flips
+            roff, moff = (Q + 1) * S1 + 2 * J, Q * S1 + 2 * J
+            own = (Q >= 1) & (Q <= TY)
+
+            def e_of(p):                     # in-pair position of the colour-c0 point on plane p
+                return np.where(((yr + p + wy) & 1) == c0, 0, 1)
+
+            first = rawplane(z0 - 1)
+            rc = np.stack([first[roff], first[roff + 1]], 1)
+            below = rawplane(z0 - 2)
+            rme = np.zeros(Q.size) if below is None else below[roff + e_of(z0 - 1)]
+            mc, mme, bk = np.zeros((Q.size, 2)), np.zeros(Q.size), np.zeros(Q.size)
+            mid = {0: np.zeros(MS), 1: np.zeros(MS)}
+            for p in range(z0 - 1, z1 + 1):
+                e = e_of(p)
+                rawc, nxt = rawplane(p), rawplane(p + 1)
+                rp = np.zeros((Q.size, 2)) if nxt is None else np.stack([nxt[roff], nxt[roff + 1]], 1)
+                g = p * S2 + yr * S1 + 2 * J
+                valid = (g >= 0) & (g < n)
+                c = rc[idx, e]
+                xl = np.where(e == 0, rawc[roff - 1], rc[:, 0])
+                xr = np.where(e == 0, rc[:, 1], rawc[roff + 2])
+                ax = d * c + c1 * (xl + xr) + cS * (rawc[roff - S1 + e] + rawc[roff + S1 + e]) + cP * (rme + rp[idx, e])
+                b0, b1 = bp[PAD + g], bp[PAD + g + 1]
+                mp = rc.copy()
+                mp[idx, e] = np.where(valid, c + wod * (np.where(e == 0, b0, b1) - ax), c)
+                bknew = np.where(e == 0, b1, b0)
+                mid[p & 1][moff], mid[p & 1][moff + 1] = mp[:, 0], mp[:, 1]
+                if p - 1 >= z0:              # pass B: the colour-1 point of plane p-1 sits where e points on plane p
+                    mprev = mid[(p - 1) & 1]
+                    c = mc[idx, e]
+                    xl = np.where(e == 0, mprev[np.maximum(moff - 1, 0)], mc[:, 0])
+                    xr = np.where(e == 0, mc[:, 1], mprev[np.minimum(moff + 2, MS - 1)])
+                    yu, yd = mprev[np.maximum(moff - S1 + e, 0)], mprev[np.minimum(moff + S1 + e, MS - 1)]
+                    ax = d * c + c1 * (xl + xr) + cS * (yu + yd) + cP * (mme + mp[idx, e])
+                    o = mc.copy()
+                    o[idx, e] = c + wod * (bk - ax)
+                    go = (p - 1) * S2 + yr * S1 + 2 * J
+                    out[go[own]], out[go[own] + 1] = o[own, 0], o[own, 1]
+                mme, mc = mc[idx, 1 - e], mp
+                rme, rc = rc[idx, 1 - e], rp
+                bk = bknew
+    assert not np.isnan(out).any()
+    return out
+
+
+@pytest.mark.parametrize("shape,TY,ZL", [((8, 8, 8), 4, 8), ((8, 8, 8), 2, 3), ((16, 16, 16), 4, 5),
+                                         ((16, 8, 16), 4, 16), ((32, 16, 32), 8, 7)])
+def test_single_pass_sweep_3d_register_pipeline_model(shape, TY, ZL):
+    A0 = sp.csr_matrix(orc.poisson_csr(shape))
+    n = A0.shape[0]
+    NZ, NY, S1 = shape
+    rs = np.random.RandomState(0)
+    x, b = rs.random_sample(n), rs.random_sample(n)
+    want = orc.rbgs(A0, b, x.copy(), 1, orc.colouring(shape, 0, n))
+    got = fused_sweep_model_3d(x, b, S1, NY, NZ, -12.0, 1.0, 1.0, 1.0, TY, ZL)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max())

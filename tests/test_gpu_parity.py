@@ -1,6 +1,8 @@
 """GPU: the CUDA path, called through the C-ABI (ctypes), against the oracle and the
 reference goldens.  Integer/index work bit-exact; fp64 within the tolerances the
 north star states (Jacobi 1e-12 relative, two-colour GS 1e-10 relative)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -199,6 +201,35 @@ def test_structured_kernels_vs_oracle(shape, gl):
         close(h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8), orc.jacobi(Al, b, y.copy(), 1, 0.8),
               JAC_RTOL, "prolong+jacobi L%d" % l)
     h.close()
+
+
+@pytest.mark.skipif(not os.environ.get("OMG_TEST_EXPERIMENTAL"),
+                    reason="experimental 3-D single-pass two-colour sweep (OMG_RB3=1): opt in with OMG_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((32, 64, 32), 2), ((128, 128, 128), 3)])
+def test_experimental_3d_single_pass_sweep(shape, gl, monkeypatch):
+    """k_st3rb (level 0 of 3-D hierarchies) against the oracle and against the two half-sweep launches."""
+    A0 = orc.poisson_csr(shape)
+    n = A0.shape[0]
+    R0 = orc.restriction(shape)
+    rs = np.random.RandomState(13)
+    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R0.shape[0])
+    col = orc.colouring(shape, 0, n)
+    y = x + R0.T.dot(e)
+    outs = {}
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv("OMG_RB3", "1")
+        else:
+            monkeypatch.delenv("OMG_RB3", raising=False)
+        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl, 8, flags=_lib.FLAG_NO_GRAPH)
+        outs[on] = [h.smooth(0, b, x, 1, "rbgs"), h.smooth(0, b, x, 2, "rbgs"),
+                    h.prolong_correct_smooth(0, b, e, x, 1, "rbgs"), h.prolong_correct_smooth(0, b, e, x, 2, "rbgs")]
+        h.close()
+    want = [orc.rbgs(sp.csr_matrix(A0), b, x.copy(), 1, col), orc.rbgs(sp.csr_matrix(A0), b, x.copy(), 2, col),
+            orc.rbgs(sp.csr_matrix(A0), b, y.copy(), 1, col), orc.rbgs(sp.csr_matrix(A0), b, y.copy(), 2, col)]
+    for i in range(4):
+        close(outs[True][i], want[i], RB_RTOL, "single-pass vs oracle, case %d" % i)
+        close(outs[True][i], outs[False][i], 1e-13, "single-pass vs half-sweeps, case %d" % i)
 
 
 def test_band_detection_reports_structure():
