@@ -162,6 +162,16 @@ def _verbose_cycle_trace(nR):
     print(nR * " " + "direct solving at level %i" % nR)                     # :233
 
 
+def _stop_rule(parameters, cycle, norm):
+    """The reference's stop test (openmg/__init__.py:121-130): a positive `cycles` caps the count, a positive
+    `threshold` stops on the residual norm; either suffices.  (omg_solve applies the same rule on the device path.)"""
+    ncyc = parameters.get('cycles', 0)
+    thr = parameters.get('threshold', 0)
+    hit_cap = ncyc > 0 and cycle >= ncyc
+    hit_norm = thr > 0 and norm < thr
+    return bool(hit_cap or hit_norm)
+
+
 def _mgSolve_pluggable(h, b, parameters):
     """mgSolve's loop (:112-148) around the Python-driven mgCycle, used when `smooth` was replaced."""
     verbose = parameters['verbose']
@@ -177,18 +187,8 @@ def _mgSolve_pluggable(h, b, parameters):
     if parameters['threshold'] <= 0 and parameters['cycles'] <= 0:
         raise ValueError("Either parameters['threshold'] or parameters['cycles'] must be > 0.")
 
-    def stop(cycle, norm):
-        cycleStop = thresholdStop = False
-        if 'cycles' in parameters and parameters['cycles'] > 0:
-            if cycle >= parameters['cycles']:
-                cycleStop = True
-        if 'threshold' in parameters:
-            if norm < parameters['threshold'] and parameters['threshold'] > 0:
-                thresholdStop = True
-        return cycleStop or thresholdStop
-
     norms = [norm]
-    while not stop(cycle, norm):
+    while not _stop_rule(parameters, cycle, norm):
         if verbose:
             print('cycle %i < cycles %i' % (cycle, parameters['cycles']))
         cycle += 1

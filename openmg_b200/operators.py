@@ -47,18 +47,13 @@ def restrictionList(problemShape, coarsestLevel, minSize, dense=False, verbose=F
     level < coarsestLevel and rows > minSize)."""
     if verbose:
         print("Generating restriction matrices; dense=%s" % dense)
-    levels = coarsestLevel + 1
-    R = []
-    level = 0
-    nextR = restriction(tuple(np.array(problemShape) // (2 ** level)), dense=dense)
-    R.append(nextR)
-    while level < levels - 1:
-        level += 1
-        nextR = restriction(tuple(np.array(problemShape) // (2 ** level)), dense=dense)
-        nNext = nextR.shape[0]
-        if nNext <= minSize:
+    fine = np.array(problemShape)
+    R = [restriction(tuple(fine), dense=dense)]                    # the first transition is unconditional
+    for level in range(1, coarsestLevel + 1):
+        candidate = restriction(tuple(fine // (2 ** level)), dense=dense)
+        if candidate.shape[0] <= minSize:                          # coarse grid would be too small: stop above it
             break
-        R.append(nextR)
+        R.append(candidate)
     return _RList(R, tuple(int(s) for s in problemShape))
 
 
@@ -162,17 +157,11 @@ def poissonnd(shape, sparse=False):
     reference's Poisson matrix (openmg/operators.py:259-276).'''
     if isinstance(shape, (int, np.integer)):
         shape = (int(shape),)
-    if len(shape) == 1:
-        toReturn = poisson1D(shape, sparse)
-    elif len(shape) == 2:
-        toReturn = poisson2D(shape, sparse)
-    elif len(shape) == 3:
-        toReturn = poisson3D(shape, sparse)
-    else:
+    generators = {1: poisson1D, 2: poisson2D, 3: poisson3D}
+    if len(shape) not in generators:
         raise ValueError('Only 1, 2 or 3 dimensions are allowed.')
-    if sparse:
-        toReturn = scipy.sparse.csr_matrix(toReturn)
-    return toReturn
+    M = generators[len(shape)](shape, sparse)
+    return scipy.sparse.csr_matrix(M) if sparse else M
 
 
 poisson = poissonnd

@@ -1,5 +1,8 @@
 '''Helper functions of the reference's `openmg.tools` (openmg/tools.py), same
 names and calling conventions.  Matrix-vector work runs on the device.'''
+import functools
+import operator
+
 import numpy as np
 import scipy.sparse as sparse
 
@@ -57,38 +60,34 @@ def flexibleMmult(x, y):
         x = x.tocsr()
     if isinstance(y, _hier.BandMatrix):
         y = y.tocsr()
-    if (not sparse.issparse(x)) and (not sparse.issparse(y)):
-        return np.dot(x, y)
-    return x * y
+    if sparse.issparse(x) or sparse.issparse(y):
+        return x * y                    # scipy matrix semantics: a matrix product
+    return np.dot(x, y)
 
 
 def dictUpdateNoClobber(updateDict, targetDict):
-    """Like dict.update, but will not clobber existing entries (openmg/tools.py:29-40).
-    >>> adict = {'a': 'A'}
-    >>> out = dictUpdateNoClobber({'b': 'B', 'c': 'C'}, adict)
-    >>> 'b' in adict and 'c' in adict
+    """Copy the entries of `updateDict` into `targetDict` unless the key is already there; returns `targetDict`
+    (the reference's helper of the same name, openmg/tools.py:29-40).
+    >>> opts = {'cycles': 3}
+    >>> dictUpdateNoClobber({'cycles': 10, 'minSize': 8}, opts) is opts
+    True
+    >>> opts == {'cycles': 3, 'minSize': 8}
     True
     """
-    for key, value in updateDict.items():
-        dictAddNoClobber(targetDict, key, value)
+    for name in updateDict:
+        targetDict.setdefault(name, updateDict[name])
     return targetDict
 
 
 def dictAddNoClobber(dictionary, key, value):
-    """Add entries to a dictionary only if they're not already there (openmg/tools.py:43-53).
-    >>> adict = {"hello": 42}
-    >>> out = dictAddNoClobber(adict, "huh", "no")
-    >>> "huh" in adict and "huh" in out
-    True
+    """dictionary[key] = value only if `key` is missing; returns the dictionary (openmg/tools.py:43-53).
+    >>> dictAddNoClobber({'omega': 0.8}, 'omega', 1.0)
+    {'omega': 0.8}
     """
-    if key not in dictionary:
-        dictionary[key] = value
+    dictionary.setdefault(key, value)
     return dictionary
 
 
 def product(iterableThing):
-    '''openmg/tools.py:56-60'''
-    out = 1
-    for thing in iterableThing:
-        out *= thing
-    return out
+    """Product of the entries, 1 for an empty iterable (openmg/tools.py:56-60)."""
+    return functools.reduce(operator.mul, iterableThing, 1)

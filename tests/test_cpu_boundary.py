@@ -106,3 +106,36 @@ def test_openmg_alias_package():
     assert openmg.mgSolve is openmg_b200.mgSolve
     import openmg.operators as ops
     assert ops is openmg_b200.operators
+
+
+def test_stop_rule_matches_the_reference_semantics():
+    """The package's stop test against a literal restatement of openmg/__init__.py:121-130 on a parameter sweep."""
+    import itertools
+    import openmg_b200 as omg
+
+    def reference_rule(parameters, cycle, norm):
+        cap = 'cycles' in parameters and parameters['cycles'] > 0 and cycle >= parameters['cycles']
+        thr = 'threshold' in parameters and parameters['threshold'] > 0 and norm < parameters['threshold']
+        return cap or thr
+
+    for cycles, threshold, cycle, norm in itertools.product((None, -1, 0, 1, 3), (None, -1.0, 0.0, 0.5),
+                                                            (1, 2, 3, 4), (0.1, 0.5, 0.7)):
+        prm = {}
+        if cycles is not None:
+            prm['cycles'] = cycles
+        if threshold is not None:
+            prm['threshold'] = threshold
+        assert omg._stop_rule(prm, cycle, norm) == reference_rule(prm, cycle, norm), (prm, cycle, norm)
+
+
+def test_restriction_list_depth_rule_host_logic(gold_operators, monkeypatch):
+    """restrictionList's depth rule is host code around the device-built R: check it on the CPU with the oracle's
+    restriction() standing in for the device call (the -m gpu suite checks the real thing)."""
+    import oracle.openmg_oracle as orc
+    import openmg_b200.operators as ops
+    monkeypatch.setattr(ops, "restriction", orc.restriction)
+    _, meta = gold_operators
+    for shape, cl, ms, shapes in meta["rlist"]:
+        Rl = ops.restrictionList(tuple(shape), cl, ms)
+        assert [list(r.shape) for r in Rl] == shapes, (shape, cl, ms)
+        assert Rl.problemShape == tuple(shape)
