@@ -91,3 +91,31 @@ def test_two_rank_gloo_gather(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_partition_properties_across_dimensions_and_rank_counts():
+    """1-D / 2-D / 3-D hierarchies on 2..8 ranks: slab levels tile the rows exactly, cuts fall on even leading
+    indices (no aggregate straddles two ranks), and the coarse slab of a rank is the image of its fine slab."""
+    cases = [((1 << 16,), 10), ((4096, 4096), 6), ((512, 1024, 512), 5), ((96, 96, 96), 3), ((1024, 1024, 1024), 6)]
+    for shape, nlev in cases:
+        lead, rows = hierarchy_rows(shape, nlev)
+        k = 2 ** len(shape)
+        for nranks in (2, 3, 4, 6, 8):
+            regular = [1] * (nlev - 1) + [0]
+            parts = [odist.partition(lead, rows, regular, nranks, r, agglomerate_below=1 << 12) for r in range(nranks)]
+            ld = parts[0][0]
+            assert all(p[0] == ld for p in parts)
+            for l in range(nlev):
+                r0 = [int(p[1][l]) for p in parts]
+                nl = [int(p[2][l]) for p in parts]
+                if l >= ld:
+                    assert r0 == [0] * nranks and nl == [rows[l]] * nranks
+                    continue
+                assert rows[l] > (1 << 12)
+                assert r0[0] == 0 and r0[-1] + nl[-1] == rows[l] and all(n > 0 for n in nl)
+                assert all(r0[i + 1] == r0[i] + nl[i] for i in range(nranks - 1))
+                stride = rows[l] // lead[l]                       # rows per leading index
+                assert all(v % (2 * stride) == 0 for v in r0 + nl)
+                if l + 1 < ld:
+                    assert [v // k for v in r0] == [int(p[1][l + 1]) for p in parts]
+                    assert [v // k for v in nl] == [int(p[2][l + 1]) for p in parts]
