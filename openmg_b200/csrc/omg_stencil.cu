@@ -49,6 +49,7 @@ struct St3 {
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
     int zlo, zhi, boundary;   // planes [zlo, zhi) in segments of ZL; `boundary`: CTA row 0 -> [0, zlo), row 1 -> [zhi, NZ)
     int use_cls;           // rows on the x/y grid boundaries get their class correction taps in-kernel (no fix-up)
+    int efly;              // MODE 2, experimental (OMG_EFLY=1): R^T e applied in registers by k_st3e, no transform pass
     ClsTab cls;
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
@@ -334,6 +335,169 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
             if (p <= z1) {
                 int k = (q - 1 + NS) % NS;      // == slot of plane z-1
                 // generic-proxy reads/writes of this slot are ordered before the async-proxy refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(full + k, span_bytes);
+                bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- prolong + Jacobi without the transform pass (EXPERIMENTAL)
+//
+// Same tiling as k_st3, MODE 2 semantics (y = x + R^T e ; xo = y + omega (b - A y)/d), pure-band levels.  Instead of
+// rewriting every staged plane in shared memory (a second pass over the span and a barrier per plane: ncu shows the
+// MODE 2 kernel bound by the shared-memory pipe), A y = A x + w A (P e) is formed in registers: all four points of a
+// 2x2 patch lie in one coarse cell C, their neighbours in C or in one of the six adjacent cells, so
+//   (A P e)_i = (d + c1 + cS) eC + c1 eX_i + cS eY_i + cP (eC + eZ)
+// with eX_i / eY_i the e of the cell of the out-of-patch x / y neighbour of point i and eZ the e of the cell below
+// (even plane) or above (odd plane).  The z-independent sums are cached over the two planes of a cell.  Neighbours
+// are taken in the FLAT index (row ends continue into the next row, plane ends into the next plane) and count as
+// zero outside the vector, exactly like the staged values.  Validated against the oracle by a numpy model
+// (tests/test_cpu_fused_sweep_model.py); NOT yet run on a GPU: selected only with OMG_EFLY=1.
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3e(const St3 P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)P.NS * P.SPAN * sizeof(double));
+    const int NS = P.NS;
+    const int tid = threadIdx.x;
+    const int z0 = P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL;
+    const int z1 = P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi);
+    const int y0 = blockIdx.x * P.TY;
+    const long long span0 = (long long)y0 * P.S1 - P.S1;
+    const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k < NS; ++k) {
+            int p = z0 - 1 + k;
+            if (p > z1) break;
+            mbar_expect_tx(full + k, span_bytes);
+            bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+        }
+    }
+
+    const int HX = P.S1 >> 1;
+    int px[ST_PPT], py[ST_PPT];
+    bool act[ST_PPT];
+#pragma unroll
+    for (int k = 0; k < ST_PPT; ++k) {
+        int p = tid + k * NT;
+        act[k] = p < P.NP;
+        p = act[k] ? p : 0;
+        py[k] = p / HX;
+        px[k] = p - py[k] * HX;
+    }
+    // e of the coarse cell of the point (xg, yg, zzg) given in flat-wrapped global coordinates; 0 outside the vector
+    auto E = [&](int xg, int yg, int zzg) -> double {
+        if (xg < 0) {
+            xg += P.S1;
+            yg -= 1;
+        } else if (xg >= P.S1) {
+            xg -= P.S1;
+            yg += 1;
+        }
+        if (yg < 0) {
+            yg += P.NYg;
+            zzg -= 1;
+        } else if (yg >= P.NYg) {
+            yg -= P.NYg;
+            zzg += 1;
+        }
+        if (zzg < 0 || zzg >= P.NZg) return 0.0;
+        return __ldg(P.e + ((long long)((zzg >> 1) - P.cz0) * P.cs1 + (yg >> 1)) * P.cs2 + (xg >> 1));
+    };
+    double q0[ST_PPT], q1[ST_PPT], q2[ST_PPT], q3[ST_PPT], wec[ST_PPT];
+#pragma unroll
+    for (int k = 0; k < ST_PPT; ++k) q0[k] = q1[k] = q2[k] = q3[k] = wec[k] = 0.0;
+    const double dsum = P.d + P.c1 + P.cS;
+
+    for (int z = z0; z < z1; ++z) {
+        const int q = z - (z0 - 1);
+        const int zz = z + P.zg0;
+        double2 ba[ST_PPT], bb[ST_PPT];
+        double zt[ST_PPT];
+#pragma unroll
+        for (int k = 0; k < ST_PPT; ++k) {
+            zt[k] = 0.0;
+            if (!act[k]) continue;
+            const int xa = 2 * px[k], ya = y0 + 2 * py[k];
+            int gi = z * P.S2 + ya * P.S1 + xa;
+            ba[k] = ldg2(P.b + gi);
+            bb[k] = ldg2(P.b + gi + P.S1);
+            if (z == z0 || !(zz & 1)) {      // first plane of a coarse cell (or of the segment): its z-independent sums
+                const double eC = E(xa, ya, zz);
+                const double eN = E(xa, ya - 1, zz), eS = E(xa, ya + 2, zz);
+                const double bs = dsum * eC;
+                q0[k] = P.w * (bs + P.c1 * E(xa - 1, ya, zz) + P.cS * eN);
+                q1[k] = P.w * (bs + P.c1 * E(xa + 2, ya, zz) + P.cS * eN);
+                q2[k] = P.w * (bs + P.c1 * E(xa - 1, ya + 1, zz) + P.cS * eS);
+                q3[k] = P.w * (bs + P.c1 * E(xa + 2, ya + 1, zz) + P.cS * eS);
+                wec[k] = P.w * eC;
+            }
+            const double eZ = (zz & 1) ? E(xa, ya, zz + 1) : E(xa, ya, zz - 1);
+            zt[k] = P.cP * (wec[k] + P.w * eZ);
+        }
+        if (z == z0) {
+            mbar_wait(full + 0, 0);
+            mbar_wait(full + 1, 0);
+        }
+        {
+            int qq = q + 1;
+            mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
+        }
+        const double *sm = stage + (size_t)((q - 1) % NS) * P.SPAN;
+        const double *sc = stage + (size_t)(q % NS) * P.SPAN;
+        const double *sp = stage + (size_t)((q + 1) % NS) * P.SPAN;
+#pragma unroll
+        for (int k = 0; k < ST_PPT; ++k) {
+            if (!act[k]) continue;
+            const int oa = (2 * py[k] + 1) * P.S1 + 2 * px[k];
+            const int ob = oa + P.S1;
+            double2 va = lds2(sc + oa), vb = lds2(sc + ob);
+            double2 vn = lds2(sc + oa - P.S1), vs = lds2(sc + ob + P.S1);
+            double2 ma = lds2(sm + oa), mb = lds2(sm + ob);
+            double2 pa = lds2(sp + oa), pb = lds2(sp + ob);
+            double la = sc[oa - 1], ra = sc[oa + 2], lb = sc[ob - 1], rb = sc[ob + 2];
+            double ax0 = P.d * va.x + P.c1 * (la + va.y) + P.cS * (vn.x + vb.x) + P.cP * (ma.x + pa.x) + (q0[k] + zt[k]);
+            double ax1 = P.d * va.y + P.c1 * (va.x + ra) + P.cS * (vn.y + vb.y) + P.cP * (ma.y + pa.y) + (q1[k] + zt[k]);
+            double ax2 = P.d * vb.x + P.c1 * (lb + vb.y) + P.cS * (va.x + vs.x) + P.cP * (mb.x + pb.x) + (q2[k] + zt[k]);
+            double ax3 = P.d * vb.y + P.c1 * (vb.x + rb) + P.cS * (va.y + vs.y) + P.cP * (mb.y + pb.y) + (q3[k] + zt[k]);
+            // y = x + w e of the own cell
+            va.x += wec[k];
+            va.y += wec[k];
+            vb.x += wec[k];
+            vb.y += wec[k];
+            const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
+            double2 oa2, ob2;
+            oa2.x = va.x + P.wod * (ba[k].x - ax0);
+            oa2.y = va.y + P.wod * (ba[k].y - ax1);
+            ob2.x = vb.x + P.wod * (bb[k].x - ax2);
+            ob2.y = vb.y + P.wod * (bb[k].y - ax3);
+            if (P.colour >= 0) {
+                bool even_match = ((zz & 1) == P.colour);
+                if (even_match) {
+                    oa2.y = va.y;
+                    ob2.x = vb.x;
+                } else {
+                    oa2.x = va.x;
+                    ob2.y = vb.y;
+                }
+            }
+            *reinterpret_cast<double2 *>(P.xo + gi) = oa2;
+            *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = ob2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int p = z - 1 + NS;
+            if (p <= z1) {
+                int k = (q - 1 + NS) % NS;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(full + k, span_bytes);
                 bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
@@ -1191,6 +1355,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->has_exc = 0;
     P->colour = -1;
     P->use_cls = 0;
+    P->efly = (xf && XH == 0 && L.kind == OMG_KIND_BAND && getenv("OMG_EFLY") != nullptr) ? 1 : 0;
     if (L.kind == OMG_KIND_BAND_EXC && L.classed && XH == 0) {
         P->use_cls = 1;
         P->cls = L.cls;
@@ -1212,6 +1377,19 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
             return false;
         }
         attr_set[P.use_cls ? 1 : 0] = true;
+    }
+    if constexpr (MODE == 2 && !SPLIT) {
+        if (P.efly && !P.use_cls) {       // experimental: prolongation applied in registers (OMG_EFLY=1)
+            static bool attr_e = false;
+            kern = k_st3e<NT>;
+            if (!attr_e) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                    cudaGetLastError();
+                    return false;
+                }
+                attr_e = true;
+            }
+        }
     }
     const int chunks = (P.NYg / P.TY) * P.XC;
     const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes

@@ -232,6 +232,39 @@ def test_experimental_3d_single_pass_sweep(shape, gl, monkeypatch):
         close(outs[True][i], outs[False][i], 1e-13, "single-pass vs half-sweeps, case %d" % i)
 
 
+@pytest.mark.skipif(not os.environ.get("OMG_TEST_EXPERIMENTAL"),
+                    reason="experimental register-side prolongation (OMG_EFLY=1): opt in with OMG_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((32, 64, 32), 2), ((128, 128, 128), 3)])
+def test_experimental_register_side_prolongation(shape, gl, monkeypatch):
+    """k_st3e (prolong + Jacobi / prolong + colour-0 half-sweep on level 0 of 3-D hierarchies) against the oracle and
+    against the transform-pass kernel, then inside whole V-cycles."""
+    A0 = sp.csr_matrix(orc.poisson_csr(shape))
+    n = A0.shape[0]
+    R0 = orc.restriction(shape)
+    rs = np.random.RandomState(17)
+    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R0.shape[0])
+    y = x + R0.T.dot(e)
+    col = orc.colouring(shape, 0, n)
+    u = rs.random_sample(n)
+    outs = {}
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv("OMG_EFLY", "1")
+        else:
+            monkeypatch.delenv("OMG_EFLY", raising=False)
+        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl, 8, flags=_lib.FLAG_NO_GRAPH)
+        bb = h.matvec(u, 0)
+        outs[on] = [h.prolong_correct_smooth(0, b, e, x, 1, "jacobi", 0.8), h.prolong_correct_smooth(0, b, e, x, 2, "jacobi", 0.8),
+                    h.prolong_correct_smooth(0, b, e, x, 1, "rbgs"),
+                    h.solve(bb, None, 1, 1, "jacobi", 0.8, 3, 0.0)[0], h.solve(bb, None, 1, 1, "rbgs", 0.8, 3, 0.0)[0]]
+        h.close()
+    close(outs[True][0], orc.jacobi(A0, b, y.copy(), 1, 0.8), JAC_RTOL, "prolong+jacobi vs oracle")
+    close(outs[True][1], orc.jacobi(A0, b, y.copy(), 2, 0.8), JAC_RTOL, "prolong+2 jacobi vs oracle")
+    close(outs[True][2], orc.rbgs(A0, b, y.copy(), 1, col), RB_RTOL, "prolong+rbgs vs oracle")
+    for i in range(5):
+        close(outs[True][i], outs[False][i], 1e-12, "register-side vs transform pass, case %d" % i)
+
+
 def test_band_detection_reports_structure():
     h = Hierarchy(orc.poisson_csr((32, 32, 32)), (32, 32, 32), 2, 8)
     i0, i1 = h.level_info(0), h.level_info(1)
