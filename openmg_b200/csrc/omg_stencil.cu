@@ -49,7 +49,6 @@ struct St3 {
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
     int zlo, zhi, boundary;   // planes [zlo, zhi) in segments of ZL; `boundary`: CTA row 0 -> [0, zlo), row 1 -> [zhi, NZ)
     int use_cls;           // rows on the x/y grid boundaries get their class correction taps in-kernel (no fix-up)
-    int efly;              // MODE 2, experimental (OMG_EFLY=1): R^T e applied in registers by k_st3e, no transform pass
     ClsTab cls;
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
 };
@@ -335,169 +334,6 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
             if (p <= z1) {
                 int k = (q - 1 + NS) % NS;      // == slot of plane z-1
                 // generic-proxy reads/writes of this slot are ordered before the async-proxy refill
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(full + k, span_bytes);
-                bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------- prolong + Jacobi without the transform pass (EXPERIMENTAL)
-//
-// Same tiling as k_st3, MODE 2 semantics (y = x + R^T e ; xo = y + omega (b - A y)/d), pure-band levels.  Instead of
-// rewriting every staged plane in shared memory (a second pass over the span and a barrier per plane: ncu shows the
-// MODE 2 kernel bound by the shared-memory pipe), A y = A x + w A (P e) is formed in registers: all four points of a
-// 2x2 patch lie in one coarse cell C, their neighbours in C or in one of the six adjacent cells, so
-//   (A P e)_i = (d + c1 + cS) eC + c1 eX_i + cS eY_i + cP (eC + eZ)
-// with eX_i / eY_i the e of the cell of the out-of-patch x / y neighbour of point i and eZ the e of the cell below
-// (even plane) or above (odd plane).  The z-independent sums are cached over the two planes of a cell.  Neighbours
-// are taken in the FLAT index (row ends continue into the next row, plane ends into the next plane) and count as
-// zero outside the vector, exactly like the staged values.  Validated against the oracle by a numpy model
-// (tests/test_cpu_fused_sweep_model.py); NOT yet run on a GPU: selected only with OMG_EFLY=1.
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3e(const St3 P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)P.NS * P.SPAN * sizeof(double));
-    const int NS = P.NS;
-    const int tid = threadIdx.x;
-    const int z0 = P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL;
-    const int z1 = P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi);
-    const int y0 = blockIdx.x * P.TY;
-    const long long span0 = (long long)y0 * P.S1 - P.S1;
-    const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
-
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int k = 0; k < NS; ++k) {
-            int p = z0 - 1 + k;
-            if (p > z1) break;
-            mbar_expect_tx(full + k, span_bytes);
-            bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
-        }
-    }
-
-    const int HX = P.S1 >> 1;
-    int px[ST_PPT], py[ST_PPT];
-    bool act[ST_PPT];
-#pragma unroll
-    for (int k = 0; k < ST_PPT; ++k) {
-        int p = tid + k * NT;
-        act[k] = p < P.NP;
-        p = act[k] ? p : 0;
-        py[k] = p / HX;
-        px[k] = p - py[k] * HX;
-    }
-    // e of the coarse cell of the point (xg, yg, zzg) given in flat-wrapped global coordinates; 0 outside the vector
-    auto E = [&](int xg, int yg, int zzg) -> double {
-        if (xg < 0) {
-            xg += P.S1;
-            yg -= 1;
-        } else if (xg >= P.S1) {
-            xg -= P.S1;
-            yg += 1;
-        }
-        if (yg < 0) {
-            yg += P.NYg;
-            zzg -= 1;
-        } else if (yg >= P.NYg) {
-            yg -= P.NYg;
-            zzg += 1;
-        }
-        if (zzg < 0 || zzg >= P.NZg) return 0.0;
-        return __ldg(P.e + ((long long)((zzg >> 1) - P.cz0) * P.cs1 + (yg >> 1)) * P.cs2 + (xg >> 1));
-    };
-    double q0[ST_PPT], q1[ST_PPT], q2[ST_PPT], q3[ST_PPT], wec[ST_PPT];
-#pragma unroll
-    for (int k = 0; k < ST_PPT; ++k) q0[k] = q1[k] = q2[k] = q3[k] = wec[k] = 0.0;
-    const double dsum = P.d + P.c1 + P.cS;
-
-    for (int z = z0; z < z1; ++z) {
-        const int q = z - (z0 - 1);
-        const int zz = z + P.zg0;
-        double2 ba[ST_PPT], bb[ST_PPT];
-        double zt[ST_PPT];
-#pragma unroll
-        for (int k = 0; k < ST_PPT; ++k) {
-            zt[k] = 0.0;
-            if (!act[k]) continue;
-            const int xa = 2 * px[k], ya = y0 + 2 * py[k];
-            int gi = z * P.S2 + ya * P.S1 + xa;
-            ba[k] = ldg2(P.b + gi);
-            bb[k] = ldg2(P.b + gi + P.S1);
-            if (z == z0 || !(zz & 1)) {      // first plane of a coarse cell (or of the segment): its z-independent sums
-                const double eC = E(xa, ya, zz);
-                const double eN = E(xa, ya - 1, zz), eS = E(xa, ya + 2, zz);
-                const double bs = dsum * eC;
-                q0[k] = P.w * (bs + P.c1 * E(xa - 1, ya, zz) + P.cS * eN);
-                q1[k] = P.w * (bs + P.c1 * E(xa + 2, ya, zz) + P.cS * eN);
-                q2[k] = P.w * (bs + P.c1 * E(xa - 1, ya + 1, zz) + P.cS * eS);
-                q3[k] = P.w * (bs + P.c1 * E(xa + 2, ya + 1, zz) + P.cS * eS);
-                wec[k] = P.w * eC;
-            }
-            const double eZ = (zz & 1) ? E(xa, ya, zz + 1) : E(xa, ya, zz - 1);
-            zt[k] = P.cP * (wec[k] + P.w * eZ);
-        }
-        if (z == z0) {
-            mbar_wait(full + 0, 0);
-            mbar_wait(full + 1, 0);
-        }
-        {
-            int qq = q + 1;
-            mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
-        }
-        const double *sm = stage + (size_t)((q - 1) % NS) * P.SPAN;
-        const double *sc = stage + (size_t)(q % NS) * P.SPAN;
-        const double *sp = stage + (size_t)((q + 1) % NS) * P.SPAN;
-#pragma unroll
-        for (int k = 0; k < ST_PPT; ++k) {
-            if (!act[k]) continue;
-            const int oa = (2 * py[k] + 1) * P.S1 + 2 * px[k];
-            const int ob = oa + P.S1;
-            double2 va = lds2(sc + oa), vb = lds2(sc + ob);
-            double2 vn = lds2(sc + oa - P.S1), vs = lds2(sc + ob + P.S1);
-            double2 ma = lds2(sm + oa), mb = lds2(sm + ob);
-            double2 pa = lds2(sp + oa), pb = lds2(sp + ob);
-            double la = sc[oa - 1], ra = sc[oa + 2], lb = sc[ob - 1], rb = sc[ob + 2];
-            double ax0 = P.d * va.x + P.c1 * (la + va.y) + P.cS * (vn.x + vb.x) + P.cP * (ma.x + pa.x) + (q0[k] + zt[k]);
-            double ax1 = P.d * va.y + P.c1 * (va.x + ra) + P.cS * (vn.y + vb.y) + P.cP * (ma.y + pa.y) + (q1[k] + zt[k]);
-            double ax2 = P.d * vb.x + P.c1 * (lb + vb.y) + P.cS * (va.x + vs.x) + P.cP * (mb.x + pb.x) + (q2[k] + zt[k]);
-            double ax3 = P.d * vb.y + P.c1 * (vb.x + rb) + P.cS * (va.y + vs.y) + P.cP * (mb.y + pb.y) + (q3[k] + zt[k]);
-            // y = x + w e of the own cell
-            va.x += wec[k];
-            va.y += wec[k];
-            vb.x += wec[k];
-            vb.y += wec[k];
-            const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
-            double2 oa2, ob2;
-            oa2.x = va.x + P.wod * (ba[k].x - ax0);
-            oa2.y = va.y + P.wod * (ba[k].y - ax1);
-            ob2.x = vb.x + P.wod * (bb[k].x - ax2);
-            ob2.y = vb.y + P.wod * (bb[k].y - ax3);
-            if (P.colour >= 0) {
-                bool even_match = ((zz & 1) == P.colour);
-                if (even_match) {
-                    oa2.y = va.y;
-                    ob2.x = vb.x;
-                } else {
-                    oa2.x = va.x;
-                    ob2.y = vb.y;
-                }
-            }
-            *reinterpret_cast<double2 *>(P.xo + gi) = oa2;
-            *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = ob2;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int p = z - 1 + NS;
-            if (p <= z1) {
-                int k = (q - 1 + NS) % NS;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(full + k, span_bytes);
                 bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
@@ -1355,7 +1191,6 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->has_exc = 0;
     P->colour = -1;
     P->use_cls = 0;
-    P->efly = (xf && XH == 0 && L.kind == OMG_KIND_BAND && getenv("OMG_EFLY") != nullptr) ? 1 : 0;
     if (L.kind == OMG_KIND_BAND_EXC && L.classed && XH == 0) {
         P->use_cls = 1;
         P->cls = L.cls;
@@ -1377,19 +1212,6 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
             return false;
         }
         attr_set[P.use_cls ? 1 : 0] = true;
-    }
-    if constexpr (MODE == 2 && !SPLIT) {
-        if (P.efly && !P.use_cls) {       // experimental: prolongation applied in registers (OMG_EFLY=1)
-            static bool attr_e = false;
-            kern = k_st3e<NT>;
-            if (!attr_e) {
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-                    cudaGetLastError();
-                    return false;
-                }
-                attr_e = true;
-            }
-        }
     }
     const int chunks = (P.NYg / P.TY) * P.XC;
     const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes
@@ -1810,63 +1632,91 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
     return true;
 }
 
-// ================================================================ 3-D single-pass two-colour sweep (EXPERIMENTAL)
+// ================================================================ 3-D single-pass two-colour sweep
 //
-// Same idea as k_st2rb one dimension up, marching in z over full-row chunks of TY rows.  An "item" is an x-pair of
-// one row; items cover rows y0-1 .. y0+TY (pass A: colour-0 point of the pair relaxed from raw planes p-1, p, p+1
-// into the mid plane p) of which rows y0 .. y0+TY-1 are stored (pass B, one plane behind: the colour-1 point of
-// plane p-1 from mid planes p-2, p-1, p).  Each thread keeps per item, across steps, the raw pair of plane p, one
-// raw element of plane p-1, the mid pair of plane p-1, one mid element of plane p-2 and the b element pass B needs:
-// z-neighbours and centres never come from shared memory, which only holds raw planes p, p+1 (+1 in flight; rows
-// y0-2 .. y0+TY+1) and mid planes p-1, p (rows y0-1 .. y0+TY).  The colour-1 point of plane p-1 sits at the same
-// in-pair position as the colour-0 point of plane p.  Rows outside [0,NY) are rows of the neighbouring plane in the
-// flat index (colour parity flips), points outside [0,n) stay zero, planes -2 and NZ+1 are all zero and not staged.
-// The index logic was validated against oracle.rbgs by a numpy model (tests/test_cpu_fused_sweep_model.py);
-// the kernel itself has NOT run on a GPU yet: it is only selected with OMG_RB3=1.
-#define ST3R_NS 3
-#define ST3R_IPT 4         // items per thread (max)
+// Both colour half-sweeps of oracle.rbgs (grid-parity colouring, colour c0 first, same-colour couplings lagged) in
+// ONE pass over x: 24 B/row instead of 2 x 24.  Same idea as k_st2rb one dimension up, marching in z over full-row
+// chunks of TY rows:
+//   pass A(p)   relaxes the colour-c0 points of plane p from the RAW planes p-1, p, p+1  -> "mid" plane p
+//   pass B(p-1) relaxes the other colour of plane p-1 from the MID planes p-2, p-1, p    -> output plane p-1
+// Pass B needs mid one row beyond the chunk, so pass A also runs on the rows y0-1 and y0+TY (recomputed, bit-identical
+// to the owner's values) and the raw planes are staged with two halo rows per side (one TMA bulk copy per plane, ring
+// of NS stages, as in k_st3).
+//
+// Work items are 2x2 (x,y) patches on even rows/columns: on every plane exactly one diagonal of a patch has the
+// colour relaxed by pass A and the other diagonal the colour relaxed by pass B one plane earlier — which diagonal is
+// the same for ALL patches of a plane (it flips from plane to plane), so the position logic is resolved by one
+// uniform branch per patch instead of per-value selects.  A thread keeps its patches in registers from plane to
+// plane (raw patch of plane p, mid patch of plane p-1, the two relaxed values of mid plane p-2, the two b values
+// pass B needs), so centres, z-neighbours and the in-patch x/y neighbours never touch shared memory: per patch and
+// plane pass A reads 2 LDS.128 (its raw patch of plane p+1) + 4 LDS.64 (out-of-patch neighbours) and writes its mid
+// patch (2 STS.128), pass B reads 4 LDS.64.  One __syncthreads per plane.
+// Flat-index semantics (openmg/operators.py:244-256: no boundary breaks): full rows make the x-wraps contiguous;
+// patch rows outside [0,NY) are rows of the neighbouring plane, so their diagonal is the flipped one; points
+// outside [0,n) are never relaxed and stay zero (the pads of the vectors).
+#define RB3_PPT 2          // full patch slots per thread
+#define RB3_NT 512
 
-struct St3R {
+struct Rb3 {
     const double *xi;
     const double *b;
     const double *e;       // coarse correction (MODE 2)
     double *xo;
     int S1, S2, NY, NZ;    // row length, plane size, rows per plane, planes
     int TY, ZL;            // rows per chunk, planes per z-segment
+    int RS, MS;            // staged raw plane (TY+4 rows) / mid plane (TY+2 rows) in doubles
     int cs1, cs2;          // coarse rows per plane, coarse row length
     int c0;                // colour relaxed first
+    ClsTab cls;            // Galerkin levels (CLS): class correction taps on the x/y grid boundaries
     double d, c1, cS, cP, wod, w;
 };
 
-template <int MODE, int NT>
-__global__ void __launch_bounds__(NT, 1) k_st3rb(const St3R P) {
+// class-correction taps of one point: planes lo/c/hi are indexed like the staged raw planes, o = the point's offset
+__device__ __forceinline__ double rb3_corr(const ClsTab &T, int cls, const double *lo, const double *c,
+                                           const double *hi, int o) {
+    double a = 0.0;
+    for (int t = 0; t < T.ntap[cls]; ++t) {
+        const int dz = T.dz[cls][t];
+        const double *pl = dz == 0 ? c : (dz > 0 ? hi : lo);
+        a += T.coef[cls][t] * pl[o + T.soff[cls][t]];
+    }
+    return a;
+}
+
+template <int MODE, bool CLS>
+__global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NS = ST3R_NS;
+    constexpr int NT = RB3_NT;
+    // class taps reach one plane down: the CLS variant keeps raw plane p-1 and mid plane p-2 resident as well
+    constexpr int NS = CLS ? 4 : 3;
+    constexpr int NM = CLS ? 3 : 2;
+    constexpr int KEEP = CLS ? 1 : 0;
+    constexpr int KS = 4 * NT;             // slot k+1 is NT patches = 2 NT / HX patch rows = 4 NT doubles further on
     const int S1 = P.S1, HX = S1 >> 1;
-    const int RS = (P.TY + 4) * S1, MS = (P.TY + 2) * S1;
+    const int RS = P.RS, MS = P.MS;
     double *raw = reinterpret_cast<double *>(smem_raw);
     double *mid = raw + (size_t)NS * RS;
-    uint64_t *full = reinterpret_cast<uint64_t *>(mid + 2 * (size_t)MS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(mid + NM * (size_t)MS);
     const int tid = threadIdx.x;
     const int y0 = (int)blockIdx.x * P.TY;
     const int z0 = (int)blockIdx.y * P.ZL;
     const int z1 = min(z0 + P.ZL, P.NZ);
-    const long long ntot = (long long)P.S2 * P.NZ;
     const uint32_t span_bytes = (uint32_t)RS * 8u;
-    const int plast = min(z1 + 1, P.NZ);          // last raw plane that exists (planes < -1 or > NZ are all zero)
+    const int pfirst = max(z0 - 2, -1);           // raw planes below -1 / above NZ are all zero and never staged
+    const int plast = min(z1 + 1, P.NZ);
+    const long long gbase = (long long)(y0 - 2) * S1;      // staged offset o <-> in-plane offset gbase + o
 
-    auto slot_of = [&](int p) { return (p - (z0 - 2)) % NS; };
-    auto issue = [&](int p) {        // p in [-1, NZ]
+    auto slot_of = [&](int p) { return (p - pfirst) % NS; };
+    auto issue = [&](int p) {
         int s_ = slot_of(p);
         mbar_expect_tx(full + s_, span_bytes);
-        bulk_g2s(raw + (size_t)s_ * RS, P.xi + (long long)p * P.S2 + (long long)(y0 - 2) * S1, span_bytes, full + s_);
+        bulk_g2s(raw + (size_t)s_ * RS, P.xi + (long long)p * P.S2 + gbase, span_bytes, full + s_);
     };
     auto wait_plane = [&](int p) {
-        int k = p - (z0 - 2);
+        int k = p - pfirst;
         mbar_wait(full + (k % NS), (uint32_t)((k / NS) & 1));
     };
-    // raw plane pl += w e[cell] on the whole staged span (rows y0-2 .. y0+TY+1; rows outside [0,NY) are rows of the
-    // neighbouring plane)
+    // MODE 2: raw plane pl += w e[cell] on the whole staged span (rows outside [0,NY) are rows of the neighbouring plane)
     auto transform = [&](int pl) {
         if constexpr (MODE == 2) {
             double *sp_ = raw + (size_t)slot_of(pl) * RS;
@@ -1897,178 +1747,256 @@ __global__ void __launch_bounds__(NT, 1) k_st3rb(const St3R P) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int p = z0 - 2; p <= z0; ++p) {
-            if (p >= -1 && p <= plast)
-                issue(p);
-            else
-                mbar_expect_tx(full + slot_of(p), 0);     // plane not staged: complete the phase so parities stay in step
-        }
+    if (tid == 0)
+        for (int p = pfirst; p < pfirst + NS && p <= plast; ++p) issue(p);
+
+    // ---- work items
+    // full slots: the TY/2 patch rows of the chunk (grid rows y0 .. y0+TY-1), 2x2 patches on even rows / columns;
+    //             pass A and pass B, all state in registers.  Slot k of thread tid is patch tid + k NT.
+    // halo item:  one x-pair of the grid row y0-1 (threads [0,HX)) or y0+TY (threads [HX,2HX)); pass A only.  These
+    //             rows may belong to the neighbouring plane (first / last chunk): their colour parity then flips.
+    const int nslots = ((P.TY >> 1) * HX) / NT;          // 1 or 2 (host: TY/2 * HX is a multiple of NT)
+    const int pj = tid / HX, pi_ = tid - pj * HX;
+    const int ro = (2 * pj + 2) * S1 + 2 * pi_;          // row a of slot 0 inside a staged raw plane; mid: ro - S1
+    const bool hact = tid < 2 * HX;
+    const bool hwhich = tid >= HX;
+    const int ho = (hwhich ? (P.TY + 2) * S1 + 2 * (tid - HX) : S1 + 2 * tid);
+    const bool hwrap = hwhich ? (y0 + P.TY == P.NY) : (y0 == 0);
+    // in-pair position the halo item relaxes on plane p: (hpar + p) & 1
+    const int hpar = (P.c0 + (hwhich ? 0 : 1) + (hwrap ? 1 : 0)) & 1;     // y0, TY even: row y0-1 is odd, y0+TY even
+
+    // carried from plane to plane, per slot: the mid patch of plane p-1, the relaxed values of mid plane p-2 and the
+    // b values of plane p-1 at the positions pass B(p-1) relaxes, the b patch of plane p (fetched one step ahead).
+    // The raw patch of plane p is re-read from the staged plane (it is resident anyway): carrying it would cost 8
+    // more registers per slot, and a single spilled register serialises the whole b prefetch behind it.
+    double2 ma[RB3_PPT], mb[RB3_PPT];
+    double ua[RB3_PPT], ub[RB3_PPT];
+    double ga[RB3_PPT], gb[RB3_PPT];
+    double2 ba[RB3_PPT], bb[RB3_PPT];
+    double hzm = 0.0, hb = 0.0;           // halo item: raw plane p-1 at the relaxed position, its b value
+#pragma unroll
+    for (int k = 0; k < RB3_PPT; ++k) {
+        ma[k] = mb[k] = ba[k] = bb[k] = make_double2(0.0, 0.0);
+        ua[k] = ub[k] = ga[k] = gb[k] = 0.0;
     }
 
-    // fixed item assignment
-    int roff[ST3R_IPT], moff[ST3R_IPT], yr[ST3R_IPT], par0[ST3R_IPT], xj[ST3R_IPT];
-    bool act[ST3R_IPT], own[ST3R_IPT];
-    const int nitems = (P.TY + 2) * HX;
-#pragma unroll
-    for (int k = 0; k < ST3R_IPT; ++k) {
-        int it = tid + k * NT;
-        act[k] = it < nitems;
-        it = act[k] ? it : 0;
-        int q = it / HX, j = it - q * HX;
-        yr[k] = y0 - 1 + q;
-        own[k] = act[k] && q >= 1 && q <= P.TY;
-        xj[k] = 2 * j;
-        roff[k] = (q + 1) * S1 + 2 * j;
-        moff[k] = q * S1 + 2 * j;
-        par0[k] = (yr[k] + ((yr[k] < 0 || yr[k] >= P.NY) ? 1 : 0) + P.c0) & 1;     // e(p) = (par0 + p) & 1
-    }
-    double2 rc[ST3R_IPT], mc[ST3R_IPT];
-    double rme[ST3R_IPT], mme[ST3R_IPT], bk[ST3R_IPT];
-
-    // prologue: registers of step p = z0-1
-    if (z0 - 2 >= -1) {
-        wait_plane(z0 - 2);
-        transform(z0 - 2);
-    }
-    wait_plane(z0 - 1);
-    transform(z0 - 1);
-    if (MODE == 2) __syncthreads();
-    {
-        const double *pm = raw + (size_t)slot_of(z0 - 2) * RS, *pc = raw + (size_t)slot_of(z0 - 1) * RS;
-#pragma unroll
-        for (int k = 0; k < ST3R_IPT; ++k) {
-            rc[k] = make_double2(0.0, 0.0);
-            mc[k] = make_double2(0.0, 0.0);
-            rme[k] = mme[k] = bk[k] = 0.0;
-            if (!act[k]) continue;
-            int e = (par0[k] + (z0 - 1)) & 1;
-            if (z0 - 2 >= -1) rme[k] = pm[roff[k] + e];
-            rc[k] = lds2(pc + roff[k]);
-        }
-    }
-    __syncthreads();        // plane z0-2 has been read by everyone
-    if (tid == 0 && z0 + 1 <= plast) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(z0 + 1);      // into the slot of plane z0-2
-    }
-
-    for (int p = z0 - 1; p <= z1; ++p) {
-        const bool has_next = (p + 1 <= plast);
-        double2 bb[ST3R_IPT];
-        bool valid[ST3R_IPT];
-#pragma unroll
-        for (int k = 0; k < ST3R_IPT; ++k) {
-            long long gi = (long long)p * P.S2 + (long long)yr[k] * S1 + xj[k];
-            valid[k] = act[k] && gi >= 0 && gi < ntot;
-            bb[k] = valid[k] ? ldg2(P.b + gi) : make_double2(0.0, 0.0);
-        }
+    // One plane step.  DG = 0: pass A relaxes (row a, .x) and (row b, .y) of every patch; DG = 1: (row a, .y) and
+    // (row b, .x).  Steps p < z0-1 only fill the register pipeline.
+    auto step = [&](auto dgc, const int p) {
+        constexpr int DG = decltype(dgc)::value;
+        constexpr int EA = DG, EB = 1 - DG;
+        auto el = [](const double2 &v, int e_) { return e_ ? v.y : v.x; };
+        const bool real = p >= z0 - 1;
+        const bool relax = real && p >= 0 && p < P.NZ;
+        const bool has_cur = (p >= pfirst && p <= plast);
+        const bool has_next = (p + 1 >= pfirst && p + 1 <= plast);
+        const int he = (hpar + p) & 1;
         if (has_next) {
             wait_plane(p + 1);
             transform(p + 1);
             if (MODE == 2) __syncthreads();
         }
-        const double *rawc = raw + (size_t)slot_of(p) * RS;
-        const double *rawn = raw + (size_t)slot_of(p + 1) * RS;
-        double *midw = mid + (size_t)(p & 1) * MS;
-        double2 rp[ST3R_IPT], mp[ST3R_IPT];
-        double bknew[ST3R_IPT];
+        const double *rawc = raw + (size_t)slot_of(max(p, pfirst)) * RS;
+        const double *rawn = raw + (size_t)slot_of(max(p + 1, pfirst)) * RS;
+        const double *rawm = raw + (size_t)slot_of(max(p - 1, pfirst)) * RS;
+        const int mq = p - z0 + 1 + NM;                                     // mid plane p lives in slot mq % NM
+        double *midw = mid + (size_t)(mq % NM) * MS - S1;                  // mid row = staged row - 1
+        const double *midp = mid + (size_t)((mq - 1) % NM) * MS - S1;
+        const double *midpp = mid + (size_t)((mq - 2) % NM) * MS - S1;
+        double2 ra[RB3_PPT], rb[RB3_PPT];      // raw patch of plane p; pass A turns it into the mid patch in place
 #pragma unroll
-        for (int k = 0; k < ST3R_IPT; ++k) {
-            rp[k] = make_double2(0.0, 0.0);
-            mp[k] = rc[k];
-            bknew[k] = 0.0;
-            if (!act[k]) continue;
-            const int e = (par0[k] + p) & 1;
-            const int o = roff[k];
-            if (has_next) rp[k] = lds2(rawn + o);
-            const double c = e ? rc[k].y : rc[k].x;
-            const double xl = e ? rc[k].x : rawc[o - 1];
-            const double xr = e ? rawc[o + 2] : rc[k].y;
-            const double yu = rawc[o - S1 + e], yd = rawc[o + S1 + e];
-            const double zp = e ? rp[k].y : rp[k].x;
-            const double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yu + yd) + P.cP * (rme[k] + zp);
-            const double bA = e ? bb[k].y : bb[k].x;
-            bknew[k] = e ? bb[k].x : bb[k].y;
-            if (valid[k]) {
-                const double nv = c + P.wod * (bA - ax);
-                if (e)
-                    mp[k].y = nv;
-                else
-                    mp[k].x = nv;
-            }
-            sts2(midw + moff[k], mp[k]);
-        }
-        __syncthreads();        // mid plane p complete
-        if (p - 1 >= z0) {
-            const double *midp = mid + (size_t)((p - 1) & 1) * MS;
-#pragma unroll
-            for (int k = 0; k < ST3R_IPT; ++k) {
-                if (!own[k]) continue;
-                const int e = (par0[k] + p) & 1;      // position of the colour-1 point of plane p-1
-                const int o = moff[k];
-                const double c = e ? mc[k].y : mc[k].x;
-                const double xl = e ? mc[k].x : midp[o - 1];
-                const double xr = e ? midp[o + 2] : mc[k].y;
-                const double yu = midp[o - S1 + e], yd = midp[o + S1 + e];
-                const double zp = e ? mp[k].y : mp[k].x;
-                const double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yu + yd) + P.cP * (mme[k] + zp);
-                const double nv = c + P.wod * (bk[k] - ax);
-                double2 ov = mc[k];
-                if (e)
-                    ov.y = nv;
-                else
-                    ov.x = nv;
-                *reinterpret_cast<double2 *>(P.xo + (long long)(p - 1) * P.S2 + (long long)yr[k] * S1 + xj[k]) = ov;
+        for (int k = 0; k < RB3_PPT; ++k) {
+            ra[k] = rb[k] = make_double2(0.0, 0.0);
+            if (has_cur && k < nslots) {
+                ra[k] = lds2(rawc + ro + k * KS);
+                rb[k] = lds2(rawc + ro + k * KS + S1);
             }
         }
+        if (relax) {
+            // ---- pass A
 #pragma unroll
-        for (int k = 0; k < ST3R_IPT; ++k) {
-            const int e = (par0[k] + p) & 1;
-            mme[k] = e ? mc[k].x : mc[k].y;
-            mc[k] = mp[k];
-            rme[k] = e ? rc[k].x : rc[k].y;
-            rc[k] = rp[k];
-            bk[k] = bknew[k];
+            for (int k = 0; k < RB3_PPT; ++k) {
+                if (k >= nslots) continue;
+                const int o = ro + k * KS;
+                const double ca = el(ra[k], EA), cb = el(rb[k], EB);
+                const double za = has_next ? rawn[o + EA] : 0.0, zb = has_next ? rawn[o + S1 + EB] : 0.0;
+                double nva, nvb;
+                {
+                    const double xl = EA ? ra[k].x : rawc[o - 1];
+                    const double xr = EA ? rawc[o + 2] : ra[k].y;
+                    const double yn = rawc[o - S1 + EA], ys = el(rb[k], EA);
+                    double ax = P.d * ca + P.c1 * (xl + xr) + P.cS * (yn + ys) + P.cP * (el(ma[k], EA) + za);
+                    if (CLS) {
+                        const int cls = ((y0 + 2 * (pj + k * (NT / HX)) == 0) ? 0 : 3) +
+                                        (EA ? (pi_ == HX - 1 ? 2 : 1) : (pi_ == 0 ? 0 : 1));
+                        if (cls != 4) ax += rb3_corr(P.cls, cls, rawm, rawc, rawn, o + EA);
+                    }
+                    nva = ca + P.wod * (el(ba[k], EA) - ax);
+                }
+                {
+                    const double xl = EB ? rb[k].x : rawc[o + S1 - 1];
+                    const double xr = EB ? rawc[o + S1 + 2] : rb[k].y;
+                    const double yn = el(ra[k], EB), ys = rawc[o + 2 * S1 + EB];
+                    double ax = P.d * cb + P.c1 * (xl + xr) + P.cS * (yn + ys) + P.cP * (el(mb[k], EB) + zb);
+                    if (CLS) {
+                        const int cls = ((y0 + 2 * (pj + k * (NT / HX)) + 1 == P.NY - 1) ? 6 : 3) +
+                                        (EB ? (pi_ == HX - 1 ? 2 : 1) : (pi_ == 0 ? 0 : 1));
+                        if (cls != 4) ax += rb3_corr(P.cls, cls, rawm, rawc, rawn, o + S1 + EB);
+                    }
+                    nvb = cb + P.wod * (el(bb[k], EB) - ax);
+                }
+                if (EA) ra[k].y = nva; else ra[k].x = nva;
+                if (EB) rb[k].y = nvb; else rb[k].x = nvb;
+            }
         }
-        __syncthreads();        // raw plane p and mid plane p-1 are free
-        if (tid == 0 && p + 3 <= plast) {
+        if (real) {
+            // mid plane p (planes -1 and NZ: nothing was relaxed, it is the all-zero raw plane)
+#pragma unroll
+            for (int k = 0; k < RB3_PPT; ++k) {
+                if (k >= nslots) continue;
+                sts2(midw + ro + k * KS, ra[k]);
+                sts2(midw + ro + k * KS + S1, rb[k]);
+            }
+        }
+        if (hact) {
+            // the halo item's row may belong to the neighbouring plane: relaxed iff that point lies inside [0,n)
+            const int hshift = hwrap ? (hwhich ? 1 : -1) : 0;
+            double2 hr = make_double2(0.0, 0.0);
+            if (has_cur) hr = lds2(rawc + ho);
+            double2 hm = hr;
+            if (real && p + hshift >= 0 && p + hshift < P.NZ) {
+                const double c = he ? hr.y : hr.x;
+                const double xl = he ? hr.x : rawc[ho - 1];
+                const double xr = he ? rawc[ho + 2] : hr.y;
+                double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (rawc[ho - S1 + he] + rawc[ho + S1 + he]) +
+                            P.cP * (hzm + (has_next ? rawn[ho + he] : 0.0));
+                if (CLS) {
+                    const int hx_ = hwhich ? tid - HX : tid;
+                    const int cls = (hwrap ? (hwhich ? 0 : 6) : 3) + (he ? (hx_ == HX - 1 ? 2 : 1) : (hx_ == 0 ? 0 : 1));
+                    if (cls != 4) ax += rb3_corr(P.cls, cls, rawm, rawc, rawn, ho + he);
+                }
+                const double nv = c + P.wod * (hb - ax);
+                if (he) hm.y = nv; else hm.x = nv;
+            }
+            if (real) sts2(midw + ho, hm);
+            hzm = he ? hr.x : hr.y;          // raw plane p at the position relaxed on plane p+1
+            if (p + 1 >= z0 - 1 && p + 1 <= z1 && p + 1 + hshift >= 0 && p + 1 + hshift < P.NZ)
+                hb = __ldg(P.b + (long long)(p + 1) * P.S2 + gbase + ho + (1 - he));
+        }
+        if (CLS && real) __syncthreads();     // the class taps of pass B read mid plane p at other threads' positions
+        {
+            // ---- pass B: the other colour of plane p-1 sits at the positions pass A just relaxed on plane p;
+            // then rotate the slot's registers and fetch b of plane p+1 (in flight during the rest of the step, the
+            // barrier and the next step's staging wait)
+            const bool doB = (p - 1 >= z0);
+            const bool bnext = (p + 1 >= max(z0 - 1, 0)) && (p + 1 <= min(z1, P.NZ - 1));
+            double *outp = P.xo + (long long)(p - 1) * P.S2 + gbase;
+            const double *bpn = P.b + (long long)(p + 1) * P.S2 + gbase;
+#pragma unroll
+            for (int k = 0; k < RB3_PPT; ++k) {
+                if (k >= nslots) continue;
+                const int o = ro + k * KS;
+                if (doB) {
+                    double2 oa = ma[k], ob = mb[k];
+                    {
+                        const double c = el(ma[k], EA);
+                        const double xl = EA ? ma[k].x : midp[o - 1];
+                        const double xr = EA ? midp[o + 2] : ma[k].y;
+                        const double yn = midp[o - S1 + EA], ys = el(mb[k], EA);
+                        double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yn + ys) + P.cP * (ua[k] + el(ra[k], EA));
+                        if (CLS) {
+                            const int cls = ((y0 + 2 * (pj + k * (NT / HX)) == 0) ? 0 : 3) +
+                                            (EA ? (pi_ == HX - 1 ? 2 : 1) : (pi_ == 0 ? 0 : 1));
+                            if (cls != 4) ax += rb3_corr(P.cls, cls, midpp, midp, midw, o + EA);
+                        }
+                        const double nv = c + P.wod * (ga[k] - ax);
+                        if (EA) oa.y = nv; else oa.x = nv;
+                    }
+                    {
+                        const double c = el(mb[k], EB);
+                        const double xl = EB ? mb[k].x : midp[o + S1 - 1];
+                        const double xr = EB ? midp[o + S1 + 2] : mb[k].y;
+                        const double yn = el(ma[k], EB), ys = midp[o + 2 * S1 + EB];
+                        double ax = P.d * c + P.c1 * (xl + xr) + P.cS * (yn + ys) + P.cP * (ub[k] + el(rb[k], EB));
+                        if (CLS) {
+                            const int cls = ((y0 + 2 * (pj + k * (NT / HX)) + 1 == P.NY - 1) ? 6 : 3) +
+                                            (EB ? (pi_ == HX - 1 ? 2 : 1) : (pi_ == 0 ? 0 : 1));
+                            if (cls != 4) ax += rb3_corr(P.cls, cls, midpp, midp, midw, o + S1 + EB);
+                        }
+                        const double nv = c + P.wod * (gb[k] - ax);
+                        if (EB) ob.y = nv; else ob.x = nv;
+                    }
+                    *reinterpret_cast<double2 *>(outp + o) = oa;
+                    *reinterpret_cast<double2 *>(outp + o + S1) = ob;
+                }
+                // pass B(p) relaxes the positions (row a, 1-EA), (row b, 1-EB)
+                ua[k] = el(ma[k], 1 - EA);
+                ub[k] = el(mb[k], 1 - EB);
+                ga[k] = el(ba[k], 1 - EA);
+                gb[k] = el(bb[k], 1 - EB);
+                ma[k] = ra[k];
+                mb[k] = rb[k];
+                if (bnext) {
+                    ba[k] = ldg2(bpn + o);
+                    bb[k] = ldg2(bpn + o + S1);
+                }
+            }
+        }
+        __syncthreads();        // raw plane p-KEEP and the oldest mid plane are free, mid plane p is complete
+        if (tid == 0 && p - KEEP >= pfirst && p - KEEP + NS <= plast) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(p + 3);       // into the slot of plane p
+            issue(p - KEEP + NS);       // into the slot of plane p-KEEP
         }
+    };
+
+    // start on a DG = 0 plane at or below z0-2: at least one fill step precedes the first relaxed plane z0-1
+    int p = z0 - 2;
+    if ((p ^ P.c0) & 1) --p;
+    if (p >= pfirst) {
+        wait_plane(p);
+        transform(p);
+        if (MODE == 2) __syncthreads();
+    }
+    for (; p <= z1; p += 2) {
+        step(std::integral_constant<int, 0>{}, p);
+        if (p + 1 <= z1) step(std::integral_constant<int, 1>{}, p + 1);
     }
 }
 
-static bool st3rb_params(Level &L, St3R *P, int *NT_out, bool need_regular) {
-    const bool on = getenv("OMG_RB3") != nullptr;       // read per call: the opt-in GPU test toggles it
-    if (!on || L.kind != OMG_KIND_BAND || L.slab || L.band.nb != 6) return false;
+static bool rb3_params(Level &L, Rb3 *P, bool *use_cls, bool need_regular) {
+    const bool off = getenv("OMG_NO_RB3") != nullptr;       // read per call: the parity test runs both paths
+    if (off || L.kind == OMG_KIND_CSR || L.slab || L.band.nb != 6) return false;
+    const bool cls = (L.kind == OMG_KIND_BAND_EXC);
+    if (cls && !L.classed) return false;             // exception rows only if the kernel corrects them itself
     const BandOp &B = L.band;
     if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return false;
     if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;
     int S1 = B.off[4], S2 = B.off[5];
-    if (S1 < 32 || (S1 & 1) || S2 % S1 != 0 || L.n % S2 != 0) return false;
+    if (S1 < 64 || (S1 & 63) || S2 % S1 != 0 || L.n % S2 != 0) return false;     // patch rows must be warp-uniform
     int NY = S2 / S1, NZ = L.n / S2;
     if ((NY & 1) || NY < 4 || NZ < 2) return false;
     if (L.colour.flat || L.colour.alpha != 3 || L.colour.s2 != S1 || L.colour.s1 != NY) return false;
     if (L.pad < S2 + 2 * S1) return false;        // plane -1 is staged from row y0-2
     if (need_regular && !(L.regular && L.reg.alpha == 3 && L.reg.fs2 == S1 && L.reg.fs1 == NY)) return false;
-    const int NT = 512;
+    const int NT = RB3_NT;
+    const int NS = cls ? 4 : 3, NM = cls ? 3 : 2;
     int TY = 0;
-    for (int t = std::min(16, NY); t >= 2; --t) {
+    for (int t = std::min(env_int("OMG_RB3_TY", 64), NY); t >= 2; --t) {
         if ((t & 1) || NY % t != 0) continue;
-        if ((t + 2) * (S1 / 2) > NT * ST3R_IPT) continue;
-        size_t smem = ((size_t)ST3R_NS * (t + 4) + 2 * (size_t)(t + 2)) * S1 * 8 + 64;
-        if (smem > 226 * 1024) continue;
+        if ((t / 2) * (S1 / 2) > NT * RB3_PPT || ((t / 2) * (S1 / 2)) % NT != 0 || S1 > NT) continue;   // whole slots; one halo item per thread
+        size_t smem = ((size_t)NS * (t + 4) + (size_t)NM * (t + 2)) * S1 * 8 + 64;
+        if (smem > 227 * 1024) continue;
         TY = t;
         break;
     }
     if (TY < 2) return false;
-    *NT_out = NT;
     P->S1 = S1;
     P->S2 = S2;
     P->NY = NY;
     P->NZ = NZ;
     P->TY = TY;
+    P->RS = (TY + 4) * S1;
+    P->MS = (TY + 2) * S1;
     P->cs1 = NY / 2;
     P->cs2 = S1 / 2;
     P->c0 = 0;
@@ -2077,7 +2005,9 @@ static bool st3rb_params(Level &L, St3R *P, int *NT_out, bool need_regular) {
     P->cS = B.coef[4];
     P->cP = B.coef[5];
     P->wod = 1.0 / B.diag;
-    {   // z-segments: 3.5 planes of overhead per segment against whole waves of one CTA per SM
+    *use_cls = cls;
+    if (cls) P->cls = L.cls;
+    {   // z-segments: 2 extra steps + ~1.5 planes of pipeline ramp per segment against whole waves of one CTA per SM
         int chunks = NY / TY, slots = std::max(g.sm_count, 1);
         int ZL = NZ;
         double best = -1.0;
@@ -2101,34 +2031,34 @@ static bool st3rb_params(Level &L, St3R *P, int *NT_out, bool need_regular) {
 }
 
 template <int MODE>
-static bool st3rb_launch(omg_hierarchy *h, const St3R &P, int NT) {
-    (void)NT;
-    static bool attr_set = false;
-    size_t smem = ((size_t)ST3R_NS * (P.TY + 4) + 2 * (size_t)(P.TY + 2)) * P.S1 * sizeof(double) + 64;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_st3rb<MODE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess) {
+static bool rb3_launch(omg_hierarchy *h, const Rb3 &P, bool cls) {
+    static bool attr_set[2] = {false, false};
+    const int NS = cls ? 4 : 3, NM = cls ? 3 : 2;
+    size_t smem = ((size_t)NS * P.RS + (size_t)NM * P.MS) * sizeof(double) + 64;
+    void (*kern)(const Rb3) = cls ? k_rb3<MODE, true> : k_rb3<MODE, false>;
+    if (!attr_set[cls]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_set = true;
+        attr_set[cls] = true;
     }
     dist_halo_wait(h);
-    k_st3rb<MODE, 512><<<dim3(P.NY / P.TY, (P.NZ + P.ZL - 1) / P.ZL), 512, smem, g.stream>>>(P);
+    kern<<<dim3(P.NY / P.TY, (P.NZ + P.ZL - 1) / P.ZL), RB3_NT, smem, g.stream>>>(P);
     return true;
 }
 
 // one full two-colour Gauss-Seidel sweep (colour 0, then colour 1) in a single pass.  xi == nullptr: probe.
 bool stencil_rb_sweep(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo) {
     St2 Q{};
-    St3R T{};
-    int NT3;
-    if (st3rb_params(L, &T, &NT3, false)) {       // experimental 3-D kernel, OMG_RB3=1 only
+    Rb3 T{};
+    bool cls3;
+    if (rb3_params(L, &T, &cls3, false)) {
         if (!xi) return true;
         T.xi = xi;
         T.b = b;
         T.xo = xo;
-        return st3rb_launch<0>(h, T, NT3);
+        return rb3_launch<0>(h, T, cls3);
     }
     if (!st2rb_params(L, &Q, false)) return false;
     if (!xi) return true;
@@ -2145,16 +2075,16 @@ bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double
                               const double *b, double *xo) {
     (void)C;
     St2 Q{};
-    St3R T{};
-    int NT3;
-    if (st3rb_params(L, &T, &NT3, true)) {        // experimental 3-D kernel, OMG_RB3=1 only
+    Rb3 T{};
+    bool cls3;
+    if (rb3_params(L, &T, &cls3, true)) {
         if (!xi) return true;
         T.xi = xi;
         T.b = b;
         T.xo = xo;
         T.e = e;
         T.w = L.Rw;
-        return st3rb_launch<2>(h, T, NT3);
+        return rb3_launch<2>(h, T, cls3);
     }
     if (!st2rb_params(L, &Q, true)) return false;
     if (!xi) return true;

@@ -252,60 +252,3 @@ def test_single_pass_sweep_3d_register_pipeline_model(shape, TY, ZL):
     want = orc.rbgs(A0, b, x.copy(), 1, orc.colouring(shape, 0, n))
     got = fused_sweep_model_3d(x, b, S1, NY, NZ, -12.0, 1.0, 1.0, 1.0, TY, ZL)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max())
-
-
-# ------------------------------------------------------------------ prolong + Jacobi with R^T e applied per cell (k_st3e)
-
-def prolong_jacobi_model_3d(x, b, e, S1, NY, NZ, d, c1, cS, cP, omega, w):
-    """y = x + R^T e ; y + omega (b - A y)/d with A y = A x + w A (P e) formed from per-cell sums, the way k_st3e does:
-    neighbours in the flat index (wraps at row / plane ends), zero outside the vector."""
-    S2 = S1 * NY
-    n = S2 * NZ
-    wod = omega / d
-    cs1, cs2 = NY // 2, S1 // 2
-    PAD = 2 * S2
-    xp = np.zeros(n + 2 * PAD)
-    xp[PAD:PAD + n] = x
-    out = np.zeros(n)
-
-    def E(xg, yg, zg):
-        if xg < 0:
-            xg, yg = xg + S1, yg - 1
-        elif xg >= S1:
-            xg, yg = xg - S1, yg + 1
-        if yg < 0:
-            yg, zg = yg + NY, zg - 1
-        elif yg >= NY:
-            yg, zg = yg - NY, zg + 1
-        if zg < 0 or zg >= NZ:
-            return 0.0
-        return e[((zg >> 1) * cs1 + (yg >> 1)) * cs2 + (xg >> 1)]
-
-    for z in range(NZ):
-        for ya in range(0, NY, 2):
-            for xa in range(0, S1, 2):
-                eC, eN, eS = E(xa, ya, z), E(xa, ya - 1, z), E(xa, ya + 2, z)
-                bs = (d + c1 + cS) * eC
-                q = [w * (bs + c1 * E(xa - 1, ya, z) + cS * eN), w * (bs + c1 * E(xa + 2, ya, z) + cS * eN),
-                     w * (bs + c1 * E(xa - 1, ya + 1, z) + cS * eS), w * (bs + c1 * E(xa + 2, ya + 1, z) + cS * eS)]
-                wec = w * eC
-                zt = cP * (wec + w * (E(xa, ya, z + 1) if (z & 1) else E(xa, ya, z - 1)))
-                for t, (dx, dy) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
-                    i = PAD + z * S2 + (ya + dy) * S1 + xa + dx
-                    ax = (d * xp[i] + c1 * (xp[i - 1] + xp[i + 1]) + cS * (xp[i - S1] + xp[i + S1])
-                          + cP * (xp[i - S2] + xp[i + S2]) + q[t] + zt)
-                    out[i - PAD] = (xp[i] + wec) + wod * (b[i - PAD] - ax)
-    return out
-
-
-@pytest.mark.parametrize("shape", [(4, 4, 4), (8, 8, 8), (8, 4, 8), (16, 8, 16)])
-def test_register_side_prolongation_model(shape):
-    A0 = sp.csr_matrix(orc.poisson_csr(shape))
-    n = A0.shape[0]
-    NZ, NY, S1 = shape
-    R = orc.restriction(shape)
-    rs = np.random.RandomState(1)
-    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R.shape[0])
-    want = orc.jacobi(A0, b, x + R.T.dot(e), 1, 0.8)
-    got = prolong_jacobi_model_3d(x, b, e, S1, NY, NZ, -12.0, 1.0, 1.0, 1.0, 0.8, R.data[0])
-    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max())

@@ -109,3 +109,72 @@ def test_config1_2d_64_reference_gs_on_device(gold_cycles):
         assert rel(x, z["2d_64/gs/%d%d/x" % (pre, post)]) <= 1e-11
         np.testing.assert_allclose(hist, z["2d_64/gs/%d%d/norms" % (pre, post)], rtol=1e-9)
         h.close()
+
+
+# ------------------------------------------------------------------ the instantiations bench.py runs, against the oracle
+
+def _oracle_cycles(shape, gl, smoother, b, ncyc, A=None, R=None):
+    if A is None:
+        A0 = orc.poisson_csr(shape)
+        R = orc.restrictionList(shape, gl - 1, 8)
+        A = orc.coeffecientList(A0, R)
+    params = {'coarsestLevel': len(R), 'preIterations': 1, 'postIterations': 1, 'verbose': False}
+    sm = orc.make_smoother(smoother, shape, 0.8)
+    xo, norms = None, []
+    for _ in range(ncyc):
+        xo, inf = orc.mgCycle(A, b, 0, R, params, initial=xo, smooth=sm)
+        norms.append(inf['norm'])
+    return xo, norms
+
+
+# thin slabs with the row widths of the benchmarks: the kernel template instantiation is chosen by the row width
+# and the level size, so these run exactly the kernels of the 512^3 (256-thread CTAs on 512- and 256-wide rows, class
+# corrections on level 1) and 1024^3 (512-thread CTAs on 1024-wide rows) benchmark lines — at sizes the oracle
+# finishes in seconds.
+@pytest.mark.parametrize("shape,gl", [((512, 8, 512), 3), ((512, 32, 512), 4), ((1024, 16, 1024), 4),
+                                      ((1024, 32, 1024), 4)])
+def test_bench_kernel_instantiations_vs_oracle(shape, gl):
+    import scipy.sparse as sp
+    A0 = orc.poisson_csr(shape)
+    R = orc.restrictionList(shape, gl - 1, 8)
+    A = orc.coeffecientList(A0, R)
+    h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8)
+    assert h.nlevels == len(A)
+    rs = np.random.RandomState(23)
+    for l in range(len(A) - 1):
+        Al = sp.csr_matrix(A[l])
+        n = Al.shape[0]
+        x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R[l].shape[0])
+        y = x + R[l].T.dot(e)
+        col = orc.colouring(shape, l, n)
+        assert rel(h.smooth(l, b, x, 2, "jacobi", 0.8), orc.jacobi(Al, b, x.copy(), 2, 0.8)) <= 1e-12
+        assert rel(h.smooth(l, b, x, 2, "rbgs"), orc.rbgs(Al, b, x.copy(), 2, col)) <= 1e-10
+        assert rel(h.residual_restrict(l, b, x), R[l].dot(b - Al.dot(x))) <= 1e-13
+        assert rel(h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8), orc.jacobi(Al, b, y.copy(), 1, 0.8)) <= 1e-12
+        assert rel(h.prolong_correct_smooth(l, b, e, x, 2, "rbgs"), orc.rbgs(Al, b, y.copy(), 2, col)) <= 1e-10
+    # whole cycles (the zero-start sweep + residual + restriction kernel only runs inside a cycle)
+    u = np.random.RandomState(0).random_sample(A0.shape[0])
+    b = A0.dot(u)
+    for smoother, tol in (("jacobi", 1e-12), ("rbgs", 1e-10)):
+        xo, norms = _oracle_cycles(shape, gl, smoother, b, 2, A, R)
+        x, cyc, norm, hist = h.solve(b, None, 1, 1, smoother, 0.8, 2, 0.0, want_history=True)
+        assert rel(x, xo) <= tol, (shape, smoother)
+        np.testing.assert_allclose(hist, norms, rtol=1e-9)
+    h.close()
+
+
+def test_config4_scaled_256_cube_vs_oracle():
+    """3-D 256^3, 5 grids, V(1,1), both smoothers: the largest cube the oracle does in about a minute."""
+    shape, gl = (256, 256, 256), 4
+    A0 = orc.poisson_csr(shape)
+    R = orc.restrictionList(shape, gl - 1, 8)
+    A = orc.coeffecientList(A0, R)
+    u = np.random.RandomState(0).random_sample(A0.shape[0])
+    b = A0.dot(u)
+    h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8)
+    for smoother, tol in (("jacobi", 1e-12), ("rbgs", 1e-10)):
+        xo, norms = _oracle_cycles(shape, gl, smoother, b, 2, A, R)
+        x, cyc, norm, hist = h.solve(b, None, 1, 1, smoother, 0.8, 2, 0.0, want_history=True)
+        assert rel(x, xo) <= tol, smoother
+        np.testing.assert_allclose(hist, norms, rtol=1e-9)
+    h.close()

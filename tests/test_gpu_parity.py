@@ -203,66 +203,42 @@ def test_structured_kernels_vs_oracle(shape, gl):
     h.close()
 
 
-@pytest.mark.skipif(not os.environ.get("OMG_TEST_EXPERIMENTAL"),
-                    reason="experimental 3-D single-pass two-colour sweep (OMG_RB3=1): opt in with OMG_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((32, 64, 32), 2), ((128, 128, 128), 3)])
-def test_experimental_3d_single_pass_sweep(shape, gl, monkeypatch):
-    """k_st3rb (level 0 of 3-D hierarchies) against the oracle and against the two half-sweep launches."""
+@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((64, 32, 64), 2), ((32, 16, 64), 2), ((128, 128, 128), 3),
+                                      ((256, 8, 256), 3)])
+def test_3d_single_pass_two_colour_sweep(shape, gl, monkeypatch):
+    """k_rb3 (both colour half-sweeps of a 3-D level in one pass, plain and fused with the prolongation) against the
+    oracle and against the two half-sweep launches (OMG_NO_RB3), on level 0 (pure band) and on Galerkin levels
+    (class-corrected boundary points)."""
     A0 = orc.poisson_csr(shape)
-    n = A0.shape[0]
-    R0 = orc.restriction(shape)
+    R = orc.restrictionList(shape, gl - 1, 8)
+    A = orc.coeffecientList(A0, R)
     rs = np.random.RandomState(13)
-    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R0.shape[0])
-    col = orc.colouring(shape, 0, n)
-    y = x + R0.T.dot(e)
+    cases = []
+    for l in range(len(A) - 1):
+        n = A[l].shape[0]
+        if n < (1 << 15):
+            continue
+        cases.append((l, rs.random_sample(n), rs.random_sample(n), rs.random_sample(R[l].shape[0])))
     outs = {}
     for on in (False, True):
         if on:
-            monkeypatch.setenv("OMG_RB3", "1")
+            monkeypatch.delenv("OMG_NO_RB3", raising=False)
         else:
-            monkeypatch.delenv("OMG_RB3", raising=False)
-        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl, 8, flags=_lib.FLAG_NO_GRAPH)
-        outs[on] = [h.smooth(0, b, x, 1, "rbgs"), h.smooth(0, b, x, 2, "rbgs"),
-                    h.prolong_correct_smooth(0, b, e, x, 1, "rbgs"), h.prolong_correct_smooth(0, b, e, x, 2, "rbgs")]
+            monkeypatch.setenv("OMG_NO_RB3", "1")
+        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+        outs[on] = [[h.smooth(l, b, x, 1, "rbgs"), h.smooth(l, b, x, 2, "rbgs"),
+                     h.prolong_correct_smooth(l, b, e, x, 1, "rbgs"), h.prolong_correct_smooth(l, b, e, x, 2, "rbgs")]
+                    for (l, x, b, e) in cases]
         h.close()
-    want = [orc.rbgs(sp.csr_matrix(A0), b, x.copy(), 1, col), orc.rbgs(sp.csr_matrix(A0), b, x.copy(), 2, col),
-            orc.rbgs(sp.csr_matrix(A0), b, y.copy(), 1, col), orc.rbgs(sp.csr_matrix(A0), b, y.copy(), 2, col)]
-    for i in range(4):
-        close(outs[True][i], want[i], RB_RTOL, "single-pass vs oracle, case %d" % i)
-        close(outs[True][i], outs[False][i], 1e-13, "single-pass vs half-sweeps, case %d" % i)
-
-
-@pytest.mark.skipif(not os.environ.get("OMG_TEST_EXPERIMENTAL"),
-                    reason="experimental register-side prolongation (OMG_EFLY=1): opt in with OMG_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((32, 64, 32), 2), ((128, 128, 128), 3)])
-def test_experimental_register_side_prolongation(shape, gl, monkeypatch):
-    """k_st3e (prolong + Jacobi / prolong + colour-0 half-sweep on level 0 of 3-D hierarchies) against the oracle and
-    against the transform-pass kernel, then inside whole V-cycles."""
-    A0 = sp.csr_matrix(orc.poisson_csr(shape))
-    n = A0.shape[0]
-    R0 = orc.restriction(shape)
-    rs = np.random.RandomState(17)
-    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R0.shape[0])
-    y = x + R0.T.dot(e)
-    col = orc.colouring(shape, 0, n)
-    u = rs.random_sample(n)
-    outs = {}
-    for on in (False, True):
-        if on:
-            monkeypatch.setenv("OMG_EFLY", "1")
-        else:
-            monkeypatch.delenv("OMG_EFLY", raising=False)
-        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl, 8, flags=_lib.FLAG_NO_GRAPH)
-        bb = h.matvec(u, 0)
-        outs[on] = [h.prolong_correct_smooth(0, b, e, x, 1, "jacobi", 0.8), h.prolong_correct_smooth(0, b, e, x, 2, "jacobi", 0.8),
-                    h.prolong_correct_smooth(0, b, e, x, 1, "rbgs"),
-                    h.solve(bb, None, 1, 1, "jacobi", 0.8, 3, 0.0)[0], h.solve(bb, None, 1, 1, "rbgs", 0.8, 3, 0.0)[0]]
-        h.close()
-    close(outs[True][0], orc.jacobi(A0, b, y.copy(), 1, 0.8), JAC_RTOL, "prolong+jacobi vs oracle")
-    close(outs[True][1], orc.jacobi(A0, b, y.copy(), 2, 0.8), JAC_RTOL, "prolong+2 jacobi vs oracle")
-    close(outs[True][2], orc.rbgs(A0, b, y.copy(), 1, col), RB_RTOL, "prolong+rbgs vs oracle")
-    for i in range(5):
-        close(outs[True][i], outs[False][i], 1e-12, "register-side vs transform pass, case %d" % i)
+    for ci, (l, x, b, e) in enumerate(cases):
+        Al = sp.csr_matrix(A[l])
+        col = orc.colouring(shape, l, Al.shape[0])
+        y = x + R[l].T.dot(e)
+        want = [orc.rbgs(Al, b, x.copy(), 1, col), orc.rbgs(Al, b, x.copy(), 2, col),
+                orc.rbgs(Al, b, y.copy(), 1, col), orc.rbgs(Al, b, y.copy(), 2, col)]
+        for i in range(4):
+            close(outs[True][ci][i], want[i], RB_RTOL, "single-pass vs oracle, L%d case %d" % (l, i))
+            close(outs[True][ci][i], outs[False][ci][i], 1e-13, "single-pass vs half-sweeps, L%d case %d" % (l, i))
 
 
 def test_band_detection_reports_structure():
