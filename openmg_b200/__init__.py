@@ -143,6 +143,7 @@ def mgSolve(A_in, b, parameters):
     infoDict = {'norm': norm, 'cycle': cycle}
     infoDict['R'] = _LazyLevels(h, 'R', nR, dense)
     infoDict['A'] = _LazyLevels(h, 'A', nR + 1, dense)
+    infoDict['A']._hierarchy = h           # mgCycle(info['A'], ...) reuses the device hierarchy
     if hist is not None:
         infoDict['norms'] = hist
     infoDict['hierarchy'] = h
@@ -205,20 +206,62 @@ def _mgSolve_pluggable(h, b, parameters):
     return result
 
 
+def _lists_match_hierarchy(h, A, R, shape):
+    """Do the caller's A / R lists describe the hierarchy the device holds (the Galerkin products of A[0] with the
+    closed-form aggregation restrictions)?  The reference's mgCycle uses whatever lists it is handed
+    (openmg/__init__.py:199-214); the device path can only honour lists equal to its own."""
+    if len(R) < h.nlevels - 1 or len(A) < h.nlevels:
+        return False
+    for l in range(h.nlevels - 1):
+        if isinstance(R, _LazyLevels):
+            break
+        want = operators.restriction(tuple(int(s) // (2 ** l) for s in shape))
+        got = scipy.sparse.csr_matrix(R[l])
+        if got.shape != want.shape or (got != want).nnz != 0:
+            return False
+    for l in range(1, h.nlevels):
+        if isinstance(A, _LazyLevels):
+            break
+        mine = h.export_A(l)
+        theirs = scipy.sparse.csr_matrix(A[l])
+        if theirs.shape != mine.shape:
+            return False
+        d = abs(theirs - mine)
+        if d.nnz and d.max() > 1e-12 * max(abs(mine).max(), 1e-300):
+            return False
+    return True
+
+
 def _hierarchy_for(A, R, parameters):
+    """The device hierarchy behind the lists handed to mgCycle: the one that produced them (infoDict['A']), the one
+    in parameters['hierarchy'], or one built from A[0] — cached per (A, R) pair, keyed by identity AND by the
+    content fingerprint of A[0], so an in-place edit of the matrix is not served from the cache."""
     h = getattr(A, '_hierarchy', None)
     if h is None:
         h = parameters.get('hierarchy', None)
-    if h is None:
-        shape = getattr(R, 'problemShape', None) or parameters.get('problemShape')
-        key = (id(A), id(R))
-        cached = _hierarchy_for._cache.get(key)
-        if cached is not None and cached[0] is A and cached[1] is R:
+    if h is not None:
+        return h
+    shape = getattr(R, 'problemShape', None) or parameters.get('problemShape')
+    depth = min(int(parameters['coarsestLevel']), len(R))       # a shallower cycle than the list allows is legal
+    A0 = A[0]
+    fp = tools.fingerprint(A0) if (scipy.sparse.issparse(A0) or isinstance(A0, BandMatrix)) else None
+    key = (id(A), id(R), depth)
+    cached = _hierarchy_for._cache.get(key)
+    if cached is not None and cached[0] is A and cached[1] is R:
+        same = (fp is not None and cached[3] == fp) or (fp is None and np.array_equal(cached[4], np.asarray(A0)))
+        if same:
             return cached[2]
-        h = Hierarchy(A[0], shape, len(R) - 1, minSize=0)
-        if h.nlevels != len(R) + 1:
-            raise ValueError("R list does not match problemShape %r" % (shape,))
-        _hierarchy_for._cache = {key: (A, R, h)}
+    if depth < 1:
+        raise ValueError("mgCycle needs at least one restriction (coarsestLevel >= 1)")
+    h = Hierarchy(A0, shape, depth - 1, minSize=0)
+    if h.nlevels != depth + 1:
+        raise ValueError("R list does not match problemShape %r" % (shape,))
+    if not _lists_match_hierarchy(h, A, R, shape):
+        raise NotImplementedError(
+            "mgCycle: the A / R lists differ from the Galerkin hierarchy of A[0] with the aggregation restrictions of "
+            "problemShape %r; the device path only runs its own hierarchy (build the lists with "
+            "operators.restrictionList / coeffecientList, or pass infoDict['A'], infoDict['R'])" % (shape,))
+    _hierarchy_for._cache = {key: (A, R, h, fp, None if fp is not None else np.array(A0, copy=True))}
     return h
 
 
@@ -236,7 +279,8 @@ def mgCycle(A, b, level, R, parameters, initial=None):
     verbose = parameters['verbose']
     h = _hierarchy_for(A, R, parameters)
     if parameters['coarsestLevel'] != h.nlevels - 1:
-        raise NotImplementedError("mgCycle: parameters['coarsestLevel'] must equal len(R)")
+        raise NotImplementedError("mgCycle: parameters['coarsestLevel'] = %r does not match the %d-level hierarchy "
+                                  "behind these lists" % (parameters['coarsestLevel'], h.nlevels))
     bf = np.asarray(b, dtype=np.float64).ravel()
     N = bf.size
     pre, post = parameters['preIterations'], parameters['postIterations']

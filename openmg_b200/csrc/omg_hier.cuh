@@ -131,6 +131,7 @@ struct omg_hierarchy {
     int64_t launches = 0;            // kernels launched since last reset
     // timings
     double t_upload_ms = 0, t_galerkin_ms = 0, t_coarse_ms = 0;
+    double coarse_defect = 0;          // max |A_L * Ainv - I| of the coarse factor that was kept
 };
 
 // allocation helpers (omg_setup.cu)

@@ -1294,9 +1294,36 @@ static int coarse_factor_blocked(omg_hierarchy *h, Level &L, int n, bool *ok) {
     return OMG_OK;
 }
 
-__global__ void k_has_nonfinite(const double *__restrict__ M, size_t count, int *__restrict__ flag) {
-    size_t i = (size_t)blockIdx.x * OMG_TPB + threadIdx.x;
-    if (i < count && !isfinite(M[i])) *flag = 1;
+// max |A*Ainv - I| over all entries (non-finite entries count as +inf): the unpivoted blocked elimination is only
+// kept when this is at rounding level, so a small-but-not-vanishing pivot of an indefinite / nonsymmetric coarse
+// operator cannot slip an inaccurate inverse into every cycle (the reference solves with pivoted SuperLU,
+// openmg/solvers.py:16-26).  One thread per (row i, column j); bit pattern of a non-negative double orders like
+// an unsigned integer.
+__global__ void k_inverse_defect(const int *__restrict__ ptr, const int *__restrict__ col,
+                                 const double *__restrict__ val, int n, const double *__restrict__ Ainv,
+                                 unsigned long long *__restrict__ worst) {
+    int j = blockIdx.x * OMG_TPB + threadIdx.x, i = blockIdx.y;
+    double r = 0.0;
+    if (j < n) {
+        double acc = (i == j) ? -1.0 : 0.0;
+        for (int p = ptr[i]; p < ptr[i + 1]; ++p) acc += val[p] * Ainv[(size_t)col[p] * n + j];
+        r = isfinite(acc) ? fabs(acc) : __longlong_as_double(0x7ff0000000000000ll);
+    }
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(worst, (unsigned long long)__double_as_longlong(r));
+}
+
+static int inverse_defect(omg_hierarchy *h, Level &L, int n, double *defect) {
+    unsigned long long *worst = nullptr, w = 0;
+    OMG_TRY(h_alloc_t(h, &worst, 1, true));
+    k_inverse_defect<<<dim3(cdiv(n, OMG_TPB), n), OMG_TPB, 0, g.stream>>>(L.ptr, L.col, L.val, n, h->Ainv, worst);
+    CUDA_TRY(cudaMemcpyAsync(&w, worst, sizeof(w), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaGetLastError());
+    h_free(h, worst);
+    long long bits = (long long)w;
+    memcpy(defect, &bits, sizeof(double));
+    return OMG_OK;
 }
 
 static int coarse_factor(omg_hierarchy *h) {
@@ -1311,14 +1338,11 @@ static int coarse_factor(omg_hierarchy *h) {
     if (!getenv("OMG_PIVOTED_FACTOR")) {
         bool ok = false;
         OMG_TRY(coarse_factor_blocked(h, L, n, &ok));
-        if (ok) {   // a vanishing pivot can also show up as inf/nan later on: check the result
-            int *flag = nullptr, f = 0;
-            OMG_TRY(h_alloc_t(h, &flag, 1, true));
-            k_has_nonfinite<<<cdiv((int64_t)n * n, OMG_TPB), OMG_TPB, 0, g.stream>>>(h->Ainv, (size_t)n * n, flag);
-            CUDA_TRY(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-            CUDA_TRY(cudaStreamSynchronize(g.stream));
-            h_free(h, flag);
-            if (f == 0) return OMG_OK;
+        if (ok) {   // no pivoting: keep the result only if A * Ainv = I to rounding (also catches inf/nan)
+            double defect = 0.0;
+            OMG_TRY(inverse_defect(h, L, n, &defect));
+            h->coarse_defect = defect;
+            if (defect <= 1e-9) return OMG_OK;
         }
         CUDA_TRY(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)n * n, g.stream));
     }
@@ -1346,6 +1370,7 @@ static int coarse_factor(omg_hierarchy *h) {
     h_free(h, piv);
     h_free(h, sing);
     if (s) return omg_set_error(OMG_ESINGULAR, "coarsest-level operator is singular");
+    OMG_TRY(inverse_defect(h, L, n, &h->coarse_defect));
     return OMG_OK;
 }
 

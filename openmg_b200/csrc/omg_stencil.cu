@@ -1656,6 +1656,7 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
 // outside [0,n) are never relaxed and stay zero (the pads of the vectors).
 #define RB3_PPT 2          // full patch slots per thread
 #define RB3_NT 512
+#define RB3_TC 3           // MODE 2: cells of the staged span per thread (max)
 
 struct Rb3 {
     const double *xi;
@@ -1716,27 +1717,64 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
         int k = p - pfirst;
         mbar_wait(full + (k % NS), (uint32_t)((k / NS) & 1));
     };
-    // MODE 2: raw plane pl += w e[cell] on the whole staged span (rows outside [0,NY) are rows of the neighbouring plane)
-    auto transform = [&](int pl) {
+    // MODE 2: y = x + R^T e is formed in the staged raw planes: plane pl += w e[cell] on the whole staged span.  A
+    // thread owns up to RB3_TC cells (coarse row x coarse column; 2 rows x 1 pair of the plane) of the span; their e
+    // values only change every other plane and are fetched one coarse plane ahead.  Rows outside [0,NY) are rows of
+    // the neighbouring plane.
+    // Cell m of thread tid is the staged row pair pj + m NT/HX, pair column pi_ (NT is a multiple of HX).
+    constexpr int TC = RB3_TC;
+    const int ncr = (P.TY + 4) >> 1;             // staged row pairs
+    const int tpj = tid / HX, tpi = tid - tpj * HX;
+    const bool firstc = (y0 == 0), lastc = (y0 + P.TY == P.NY);
+    double enxt[TC];
+    int eplane_nxt = -(1 << 30);       // the raw plane enxt was fetched for
+    auto load_e = [&](int pl, double *ev) {      // w e of this thread's cells for raw plane pl
         if constexpr (MODE == 2) {
-            double *sp_ = raw + (size_t)slot_of(pl) * RS;
-            const int npairs = (P.TY + 4) * HX;
-            for (int t = tid; t < npairs; t += NT) {
-                int rq = t / HX, jj = t - rq * HX;
-                int yy = y0 - 2 + rq, zz = pl;
-                if (yy < 0) {
-                    yy += P.NY;
-                    zz -= 1;
-                } else if (yy >= P.NY) {
-                    yy -= P.NY;
-                    zz += 1;
+            const double *ep = P.e + tpi;
+#pragma unroll
+            for (int m = 0; m < TC; ++m) {
+                const int cr = tpj + m * (NT / HX);
+                int zz = pl, crow = (y0 >> 1) - 1 + cr;
+                if (firstc && cr == 0) {          // rows -2, -1: the last coarse row of the plane below
+                    crow = P.cs1 - 1;
+                    zz = pl - 1;
                 }
-                if (zz < 0 || zz >= P.NZ) continue;
-                double v = P.w * __ldg(P.e + ((long long)(zz >> 1) * P.cs1 + (yy >> 1)) * P.cs2 + jj);
-                double2 x = lds2(sp_ + rq * S1 + 2 * jj);
-                x.x += v;
-                x.y += v;
-                sts2(sp_ + rq * S1 + 2 * jj, x);
+                if (lastc && cr == ncr - 1) {     // rows NY, NY+1: the first coarse row of the plane above
+                    crow = 0;
+                    zz = pl + 1;
+                }
+                ev[m] = 0.0;
+                if (cr < ncr && zz >= 0 && zz < P.NZ)
+                    ev[m] = P.w * __ldg(ep + ((zz >> 1) * P.cs1 + crow) * P.cs2);
+            }
+        }
+    };
+    auto apply_e = [&](int pl, const double *ev) {
+        if constexpr (MODE == 2) {
+            double *sp_ = raw + (size_t)slot_of(pl) * RS + 2 * tpj * S1 + 2 * tpi;
+#pragma unroll
+            for (int m = 0; m < TC; ++m) {
+                if (tpj + m * (NT / HX) >= ncr) continue;
+                double *q = sp_ + m * KS;
+                double2 x0 = lds2(q), x1 = lds2(q + S1);
+                x0.x += ev[m];
+                x0.y += ev[m];
+                x1.x += ev[m];
+                x1.y += ev[m];
+                sts2(q, x0);
+                sts2(q + S1, x1);
+            }
+        }
+    };
+    // wrapped staged rows shift the plane by one, so a thread's cells do not all change coarse plane on the same
+    // step: simply reload e for every plane (L1/L2 hits), one plane ahead of its use
+    auto transform = [&](int pl) {       // raw plane pl has landed: add its e (fetched during the previous call)
+        if constexpr (MODE == 2) {
+            if (eplane_nxt != pl) load_e(pl, enxt);
+            apply_e(pl, enxt);
+            if (pl + 1 <= plast) {
+                load_e(pl + 1, enxt);
+                eplane_nxt = pl + 1;
             }
         }
     };
@@ -1791,11 +1829,7 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
         const bool has_cur = (p >= pfirst && p <= plast);
         const bool has_next = (p + 1 >= pfirst && p + 1 <= plast);
         const int he = (hpar + p) & 1;
-        if (has_next) {
-            wait_plane(p + 1);
-            transform(p + 1);
-            if (MODE == 2) __syncthreads();
-        }
+        if (MODE != 2 && has_next) wait_plane(p + 1);      // MODE 2: waited for and transformed during the previous step
         const double *rawc = raw + (size_t)slot_of(max(p, pfirst)) * RS;
         const double *rawn = raw + (size_t)slot_of(max(p + 1, pfirst)) * RS;
         const double *rawm = raw + (size_t)slot_of(max(p - 1, pfirst)) * RS;
@@ -1932,8 +1966,10 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
                 // pass B(p) relaxes the positions (row a, 1-EA), (row b, 1-EB)
                 ua[k] = el(ma[k], 1 - EA);
                 ub[k] = el(mb[k], 1 - EB);
-                ga[k] = el(ba[k], 1 - EA);
-                gb[k] = el(bb[k], 1 - EB);
+                // (opaque moves: if ga/gb merely aliased halves of ba/bb, the b registers could not be reloaded in place
+                // and the loop back-edge would have to move b values that are still in flight)
+                asm volatile("mov.f64 %0, %1;" : "=d"(ga[k]) : "d"(el(ba[k], 1 - EA)));
+                asm volatile("mov.f64 %0, %1;" : "=d"(gb[k]) : "d"(el(bb[k], 1 - EB)));
                 ma[k] = ra[k];
                 mb[k] = rb[k];
                 if (bnext) {
@@ -1941,6 +1977,10 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
                     bb[k] = ldg2(bpn + o + S1);
                 }
             }
+        }
+        if (MODE == 2 && p + 2 >= pfirst && p + 2 <= plast) {
+            wait_plane(p + 2);      // one plane ahead, so that the barrier below publishes the transformed plane
+            transform(p + 2);
         }
         __syncthreads();        // raw plane p-KEEP and the oldest mid plane are free, mid plane p is complete
         if (tid == 0 && p - KEEP >= pfirst && p - KEEP + NS <= plast) {
@@ -1952,10 +1992,15 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
     // start on a DG = 0 plane at or below z0-2: at least one fill step precedes the first relaxed plane z0-1
     int p = z0 - 2;
     if ((p ^ P.c0) & 1) --p;
-    if (p >= pfirst) {
+    if (MODE == 2) {
+        for (int q = p; q <= p + 1; ++q)
+            if (q >= pfirst && q <= plast) {
+                wait_plane(q);
+                transform(q);
+            }
+        __syncthreads();
+    } else if (p >= pfirst) {
         wait_plane(p);
-        transform(p);
-        if (MODE == 2) __syncthreads();
     }
     for (; p <= z1; p += 2) {
         step(std::integral_constant<int, 0>{}, p);

@@ -9,28 +9,58 @@ import scipy.sparse as sparse
 from . import hierarchy as _hier
 
 _OP_CACHE = {}
+_FULL_CHECKSUM_NNZ = 1 << 22
+
+
+def fingerprint(A):
+    """A cheap content fingerprint of a matrix, so that a cached device copy is not reused after the caller
+    changed the matrix in place (the reference always reads the live matrix).  Sparse matrices up to 2^22
+    stored entries: Adler-32 over data, indices and indptr (exact for all practical purposes).  Larger ones:
+    the sum of the values plus Adler-32 over a strided sample of 2^20 entries — a change confined to entries
+    outside the sample that also preserves the sum goes unnoticed; call `invalidate_cache(A)` after such an
+    edit."""
+    import zlib
+    if isinstance(A, _hier.BandMatrix):
+        return (float(A.diag), tuple(int(o) for o in A.offsets), tuple(float(c) for c in A.coeffs))
+    if sparse.issparse(A):
+        if A.format not in ('csr', 'csc', 'coo', 'bsr'):
+            return None                  # formats without flat arrays (lil, dok): never reuse a cached copy
+        arrs = [A.data] + [getattr(A, n) for n in ('indices', 'indptr', 'row', 'col') if hasattr(A, n)]
+        if A.nnz <= _FULL_CHECKSUM_NNZ:
+            return tuple(zlib.adler32(np.ascontiguousarray(a).view(np.uint8)) for a in arrs)
+        step = max(1, A.nnz >> 20)
+        return (float(np.sum(A.data)),) + tuple(zlib.adler32(np.ascontiguousarray(a[::step]).view(np.uint8))
+                                                 for a in arrs)
+    return None
+
+
+def invalidate_cache(A=None):
+    """Forget the cached device copy of A (all cached copies if A is None)."""
+    if A is None:
+        _OP_CACHE.clear()
+        return
+    for key in [k for k, ent in _OP_CACHE.items() if ent[0] is A]:
+        del _OP_CACHE[key]
 
 
 def _operator_for(A, factor=False):
-    """Device copy of A, cached by object identity (+ nnz/shape so a mutated
-    pattern is re-uploaded)."""
-    if isinstance(A, _hier.BandMatrix):
-        key = (id(A), A.n, factor)
-    elif sparse.issparse(A):
-        key = (id(A), A.shape, A.nnz, factor)
-    else:
+    """Device copy of A, cached by object identity and verified by content: a fingerprint for sparse / band
+    matrices, an element-wise comparison for dense arrays (both are mutable in place)."""
+    structured = isinstance(A, _hier.BandMatrix) or sparse.issparse(A)
+    if not structured:
         A = np.asarray(A)
-        key = (id(A), A.shape, None, factor)
+    key = (id(A), tuple(A.shape) if hasattr(A, 'shape') else A.n, factor)
+    fp = fingerprint(A) if structured else None
     ent = _OP_CACHE.get(key)
     if ent is not None and ent[0] is A:
-        if sparse.issparse(A) or isinstance(A, _hier.BandMatrix):
+        if structured and fp is not None and ent[3] == fp:
             return ent[1]
-        if np.array_equal(ent[2], A):      # dense arrays are mutable in place: verify
+        if not structured and np.array_equal(ent[2], A):
             return ent[1]
     op = _hier.Operator(A, factor=factor)
     if len(_OP_CACHE) > 16:
         _OP_CACHE.clear()
-    _OP_CACHE[key] = (A, op, None if (sparse.issparse(A) or isinstance(A, _hier.BandMatrix)) else A.copy())
+    _OP_CACHE[key] = (A, op, None if structured else A.copy(), fp)
     return op
 
 

@@ -225,6 +225,57 @@ def test_mgcycle_api_with_lists():
     assert np.isclose(i1['norm'], i2['norm'], rtol=1e-10, atol=1e-14)
 
 
+def test_mgcycle_lists_semantics():
+    """The reference's mgCycle runs on whatever A / R lists it is handed (openmg/__init__.py:199-214).  The device
+    path accepts lists that equal its own hierarchy (also a shallower coarsestLevel than the lists allow, and the
+    lists mgSolve returned), refuses anything else loudly, and never serves a stale device copy after the caller
+    edited the matrix in place."""
+    shape = (16, 16)
+    A_in = sp.csr_matrix(operators.poisson(shape))
+    _, b = seeded_problem(A_in)
+    R = operators.restrictionList(shape, 1, 2)
+    A = operators.coeffecientList(A_in, R)
+    assert len(R) == 2
+    sm = orc.make_smoother('rbgs', shape, 0.8)
+    base = {'preIterations': 1, 'postIterations': 1, 'verbose': False, 'problemShape': shape, 'smoother': 'rbgs'}
+    Ro = orc.restrictionList(shape, 1, 2)
+    Ao = orc.coeffecientList(A_in, Ro)
+    for depth in (2, 1):              # depth 1: direct solve on level 1 although the lists go deeper
+        params = dict(base, coarsestLevel=depth)
+        u1, info = openmg.mgCycle(A, b, 0, R, params)
+        u2, info2 = orc.mgCycle(Ao, b, 0, Ro, params, smooth=sm)
+        np.testing.assert_allclose(u1, u2, rtol=1e-10)
+        assert np.isclose(info['norm'], info2['norm'], rtol=1e-9)
+    # lists that are not the Galerkin hierarchy of A[0]: refused, not silently replaced
+    A_bad = list(A)
+    A_bad[1] = A[1] * 1.5
+    with pytest.raises(NotImplementedError):
+        openmg.mgCycle(A_bad, b, 0, R, dict(base, coarsestLevel=2))
+    R_bad = list(R)
+    R_bad[0] = R[0] * 2.0
+    with pytest.raises(NotImplementedError):
+        openmg.mgCycle(A, b, 0, R_bad, dict(base, coarsestLevel=2))
+    # the lists mgSolve hands back drive mgCycle on the same device hierarchy
+    x, info = openmg.mgSolve(A_in, b, dict(base, gridLevels=2, minSize=2, cycles=2, threshold=0, giveInfo=True))
+    params = dict(base, coarsestLevel=len(info['R']))
+    y, _ = openmg.mgCycle(info['A'], b, 0, info['R'], params, initial=x)
+    z, _ = orc.mgCycle(Ao, b, 0, Ro, params, initial=np.array(x), smooth=sm)
+    np.testing.assert_allclose(y, z, rtol=1e-10)
+    # in-place edit of the matrix between calls: the cached device copies must not be reused
+    A_in2 = A_in.copy()
+    xr = np.random.RandomState(5).random_sample(A_in2.shape[0])
+    r1 = tools.getresidual(b, A_in2, xr, xr.size).ravel()
+    A_in2.data *= 2.0
+    r2 = tools.getresidual(b, A_in2, xr, xr.size).ravel()
+    np.testing.assert_allclose(r2, b - A_in2.dot(xr), rtol=1e-13)
+    assert np.abs(r2 - r1).max() > 1e-3
+    lists = [A_in2] + list(operators.coeffecientList(A_in2, R)[1:])
+    u1, _ = openmg.mgCycle(lists, b, 0, R, dict(base, coarsestLevel=2))
+    A_in2.data *= 0.5                      # lists[0] edited in place: the levels below no longer match
+    with pytest.raises(NotImplementedError):
+        openmg.mgCycle(lists, b, 0, R, dict(base, coarsestLevel=2))
+
+
 def test_simple_demo_trace():
     # openmg_usage_demo.py:27-41 with the reference's smoother: residual trace of today's code
     N = 100

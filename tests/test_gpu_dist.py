@@ -1,9 +1,12 @@
-"""GPU, 2 ranks (skipped on a single-GPU box): row-slab sharding with NCCL halo exchange gives
-the same iterates as the single-GPU path."""
+"""GPU, 2/4/8 ranks (skipped when the box has fewer GPUs): row-slab sharding with the peer-memory halo exchange gives
+the same iterates as the single-GPU (replicated) path and as the oracle.  With 4 and 8 ranks the interior ranks have
+both neighbours; the 1024-wide shape runs the 512-thread kernels of the 8-GPU 1024^3 benchmark line on several slab
+levels."""
 import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -19,14 +22,20 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("shape,gl,agg", [((64, 64, 64), 3, 4096), ((128, 128, 128), 4, 1 << 16),
-                                          ((256, 256), 4, 1024), ((1024, 1024), 5, 4096), ((65536,), 8, 1024)])
-def test_slab_sharding_matches_single_gpu(shape, gl, agg):
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"),
+CASES = [((64, 64, 64), 3, 4096), ((128, 128, 128), 4, 1 << 16), ((256, 256), 4, 1024), ((1024, 1024), 5, 4096),
+         ((65536,), 8, 1024), ((64, 32, 1024), 4, 4096), ((128, 16, 1024), 4, 1 << 14)]
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+@pytest.mark.parametrize("shape,gl,agg", CASES)
+def test_slab_sharding_matches_single_gpu_and_oracle(shape, gl, agg, nproc):
+    if _ngpus() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    if shape[0] // (1 << (gl - 1)) < 1 or shape[0] % (2 * nproc) != 0:
+        pytest.skip("leading extent does not split into %d even slabs" % nproc)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(29541 + nproc), os.path.join(ROOT, "tools", "dist_check.py"),
            "--shape"] + [str(s) for s in shape] + ["--gl", str(gl), "--agg", str(agg)] + (
-               ["--oracle"] if int(__import__("numpy").prod(shape)) <= 262144 else [])
+               ["--oracle"] if int(np.prod(shape)) <= (1 << 22) else [])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
