@@ -160,6 +160,13 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
               int pre, int post, int smoother, double omega, int cycles, double threshold,
               int *cycles_done, double *final_norm, double *norm_hist, int hist_cap);
 
+/* Diagnostics of the last omg_solve / of the setup: host_syncs = stream synchronisations the cycle loop issued
+ * (a thresholded solve tests its stop rule on the device, openmg/__init__.py:118-138, and synchronises once per
+ * batch of cycles, not once per cycle); coarse_defect = max |A_L * Ainv - I| of the coarse factor
+ * (openmg/solvers.py:16-26 solves with pivoted SuperLU; the device inverse is only kept unpivoted when this is
+ * at rounding level). */
+int omg_solve_stats(const omg_hierarchy *h, int64_t *host_syncs, double *coarse_defect);
+
 /* One mgCycle(A, b, level, R, parameters, initial) (openmg/__init__.py:151-236) entered at
  * `level`: b_host / x_host have n_level entries; x_host is the initial iterate when
  * has_initial, and receives uOut.  norm = ||b - A_level uOut||_2 (:227; 0 on the coarsest, :232). */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "omg_solve": (ctypes.c_int, [c_h, c_f64p, c_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_double, ctypes.c_int, ctypes.c_double, c_i32p, c_f64p, c_f64p,
                                  ctypes.c_int]),
+    "omg_solve_stats": (ctypes.c_int, [c_h, c_i64p, c_f64p]),
     "omg_cycle": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_int, ctypes.c_double, c_f64p]),
     "omg_set_rhs": (ctypes.c_int, [c_h, c_f64p]),

@@ -112,6 +112,9 @@ void omg_hierarchy_destroy(omg_hierarchy *h) {
     dist_peer_teardown(h);
     for (auto &kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto &kv : h->gated)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (h->stop_host) cudaFreeHost(h->stop_host);
     for (void *p : h->allocs) cudaFree(p);
     if (h->norm2_host) cudaFreeHost(h->norm2_host);
     delete h;
@@ -447,6 +450,129 @@ static int exec_cycle(omg_hierarchy *h, CycleCfg cfg) {
     return OMG_OK;
 }
 
+// ---- device-side stop rule (thresholded solves without a host round trip per cycle)
+
+__global__ void k_stop_gate(cudaGraphConditionalHandle hnd, const StopState *s) {
+    cudaGraphSetConditional(hnd, s->done ? 0u : 1u);
+}
+
+// after a cycle and its norm: count it, record the norm, apply openmg/__init__.py:121-130
+__global__ void k_stop_update(StopState *s, const double *norm2, double *hist) {
+    const double nv = sqrt(*norm2);
+    const int c = ++s->cycle;
+    s->norm = nv;
+    if (hist && c <= s->hist_cap) hist[c - 1] = nv;
+    const bool cycleStop = s->max_cycles > 0 && c >= s->max_cycles;
+    const bool thresholdStop = s->threshold > 0.0 && nv < s->threshold;
+    if (cycleStop || thresholdStop) s->done = 1;
+}
+
+// graph = [gate kernel] -> IF(!done) { one V-cycle, residual norm, stop update }
+static int exec_gated_cycle(omg_hierarchy *h, CycleCfg cfg) {
+    cfg.cur0 = h->cur0;
+    cfg.with_norm = 1;
+    auto it = h->gated.find(cfg);
+    if (it == h->gated.end()) {
+        int64_t l0 = h->launches;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaGraphCreate(&graph, 0));
+        cudaGraphConditionalHandle hnd;
+        CUDA_TRY(cudaGraphConditionalHandleCreate(&hnd, graph, 0, 0));
+        cudaGraphNode_t gate = nullptr, cond = nullptr;
+        {
+            cudaGraphNodeParams kp = {cudaGraphNodeTypeKernel};
+            const StopState *sp = h->stop_dev;
+            void *args[2] = {(void *)&hnd, (void *)&sp};
+            kp.kernel.func = (void *)k_stop_gate;
+            kp.kernel.gridDim = dim3(1);
+            kp.kernel.blockDim = dim3(1);
+            kp.kernel.kernelParams = args;
+            CUDA_TRY(cudaGraphAddNode(&gate, graph, nullptr, 0, &kp));
+        }
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = hnd;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        CUDA_TRY(cudaGraphAddNode(&cond, graph, &gate, 1, &cp));
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        CUDA_TRY(cudaStreamBeginCaptureToGraph(g.stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        int rc = run_cycle(h, cfg);
+        k_stop_update<<<1, 1, 0, g.stream>>>(h->stop_dev, h->norm2_dev, h->hist_dev);
+        cudaGraph_t got = nullptr;
+        cudaError_t e = cudaStreamEndCapture(g.stream, &got);
+        if (rc != OMG_OK || e != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            if (rc != OMG_OK) return rc;
+            return omg_set_error(OMG_ECUDA, "gated graph capture failed: %s", cudaGetErrorString(e));
+        }
+        CachedGraph cg;
+        e = cudaGraphInstantiate(&cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "gated graph instantiate failed: %s", cudaGetErrorString(e));
+        cg.cur0_after = h->cur0;
+        cg.launches = h->launches - l0 + 2;
+        h->launches = l0;
+        h->cur0 = cfg.cur0;
+        it = h->gated.insert({cfg, cg}).first;
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second.exec, g.stream));
+    h->cur0 = it->second.cur0_after;
+    h->launches += it->second.launches;
+    return OMG_OK;
+}
+
+// The cycle loop of mgSolve with the stop test on the device: cycles are enqueued in growing batches (1, 2, 4, ...
+// up to 16); once the test fires the remaining graphs of the batch skip their body.  One stream synchronisation per
+// batch instead of one per cycle; the result buffer follows from the number of cycles that really ran.
+static int solve_gated(omg_hierarchy *h, CycleCfg cfg, int cycles, double threshold, int *cycle_out, double *norm_out,
+                       double *norm_hist, int hist_cap) {
+    if (!h->stop_dev) {
+        OMG_TRY(h_alloc_t(h, &h->stop_dev, 1, true));
+        CUDA_TRY(cudaMallocHost((void **)&h->stop_host, sizeof(StopState)));
+    }
+    const int want_hist = (norm_hist && hist_cap > 0) ? hist_cap : 0;
+    if (want_hist > h->hist_dev_cap) {
+        if (h->hist_dev) h_free(h, h->hist_dev);
+        h->hist_dev = nullptr;
+        // the gated graphs captured the old buffer address
+        for (auto &kv : h->gated)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        h->gated.clear();
+        OMG_TRY(h_alloc_t(h, &h->hist_dev, (size_t)want_hist, true));
+        h->hist_dev_cap = want_hist;
+    }
+    const bool both_disabled = (threshold <= 0.0 && cycles <= 0);
+    StopState st{threshold, 0.0, both_disabled ? 1 : cycles, 0, 0, want_hist ? std::min(want_hist, h->hist_dev_cap) : 0};
+    *h->stop_host = st;
+    CUDA_TRY(cudaMemcpyAsync(h->stop_dev, h->stop_host, sizeof(StopState), cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));     // stop_host is reused as the read-back buffer below
+    std::vector<int> cur0_seq(1, h->cur0);          // iterate buffer after k executed cycles
+    int issued = 0, batch = 1;
+    for (;;) {
+        if (cycles > 0) batch = std::min(batch, cycles - issued);
+        for (int i = 0; i < batch; ++i) {
+            OMG_TRY(exec_gated_cycle(h, cfg));
+            cur0_seq.push_back(h->cur0);
+        }
+        issued += batch;
+        CUDA_TRY(cudaMemcpyAsync(h->stop_host, h->stop_dev, sizeof(StopState), cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        h->host_syncs++;
+        if (h->stop_host->done || (cycles > 0 && issued >= cycles)) break;
+        batch = std::min(batch * 2, 16);
+    }
+    const int ran = h->stop_host->cycle;
+    h->cur0 = cur0_seq[std::min<size_t>((size_t)ran, cur0_seq.size() - 1)];
+    *cycle_out = ran;
+    *norm_out = h->stop_host->norm;
+    if (want_hist && ran > 0) {
+        CUDA_TRY(cudaMemcpyAsync(norm_hist, h->hist_dev, sizeof(double) * (size_t)std::min(ran, want_hist),
+                                 cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+    }
+    return OMG_OK;
+}
+
 static int read_norm(omg_hierarchy *h, double *norm) {
     CUDA_TRY(cudaMemcpyAsync(h->norm2_host, h->norm2_dev, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -494,6 +620,16 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
     double norm = 0.0;
     // do at least one cycle (openmg/__init__.py:112)
     bool both_disabled = (threshold <= 0.0 && cycles <= 0);
+    h->host_syncs = 0;
+    if (every && !(h->flags & OMG_FLAG_NO_GRAPH)) {
+        // a norm after every cycle (threshold stop, or a residual history was asked for): stop test on the device
+        OMG_TRY(solve_gated(h, cfg, cycles, threshold, &cycle, &norm, norm_hist, hist_cap));
+        if (cycles_done) *cycles_done = cycle;
+        if (final_norm) *final_norm = norm;
+        if (both_disabled)      // ValueError raised after the first cycle (:118-119)
+            return omg_set_error(OMG_EINVAL, "Either parameters['threshold'] or parameters['cycles'] must be > 0.");
+        return download_x(h, x_host);
+    }
     for (;;) {
         // without a threshold the norm is only needed after the last cycle (:140-141)
         bool last_known = !every && (both_disabled || cycle + 1 >= cycles);
@@ -502,6 +638,7 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
         ++cycle;
         if (cfg.with_norm) {
             OMG_TRY(read_norm(h, &norm));
+            h->host_syncs++;
             if (norm_hist && cycle <= hist_cap) norm_hist[cycle - 1] = norm;
         }
         if (both_disabled) {   // ValueError raised after the first cycle (:118-119)
@@ -516,6 +653,13 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
     if (cycles_done) *cycles_done = cycle;
     if (final_norm) *final_norm = norm;
     return download_x(h, x_host);
+}
+
+int omg_solve_stats(const omg_hierarchy *h, int64_t *host_syncs, double *coarse_defect) {
+    CHECK_H(h);
+    if (host_syncs) *host_syncs = h->host_syncs;
+    if (coarse_defect) *coarse_defect = h->coarse_defect;
+    return OMG_OK;
 }
 
 int omg_cycle(omg_hierarchy *h, int level, const double *b_host, double *x_host, int has_initial, int pre,

@@ -89,6 +89,18 @@ struct CachedGraph {
     int64_t launches = 0;
 };
 
+// Device-side stop rule of mgSolve (openmg/__init__.py:118-138): the state lives in device memory, every cycle of a
+// thresholded solve is wrapped in an IF node of its CUDA graph, so the host enqueues cycles without reading anything
+// back in between.
+struct StopState {
+    double threshold;     // <= 0: no residual test
+    double norm;          // ||b - A x||_2 after the last executed cycle
+    int max_cycles;       // <= 0: no cycle cap
+    int cycle;            // cycles executed
+    int done;
+    int hist_cap;
+};
+
 struct ProfRec {
     const char *name;
     int level;
@@ -128,6 +140,11 @@ struct omg_hierarchy {
     // state
     int cur0 = 0;                    // level-0 iterate lives in xa (0) or xb (1)
     std::map<CycleCfg, CachedGraph> graphs;
+    std::map<CycleCfg, CachedGraph> gated;      // the same cycles behind the device-side stop test
+    StopState *stop_dev = nullptr, *stop_host = nullptr;     // device / pinned
+    double *hist_dev = nullptr;
+    int hist_dev_cap = 0;
+    int64_t host_syncs = 0;          // stream synchronisations issued by the last omg_solve (diagnostic)
     int64_t launches = 0;            // kernels launched since last reset
     // timings
     double t_upload_ms = 0, t_galerkin_ms = 0, t_coarse_ms = 0;

@@ -272,6 +272,12 @@ class Hierarchy(_Handle):
                                 f64(hist) if hist is not None else None, cap if hist is not None else 0))
         return out, done.value, norm.value, (hist[:done.value].copy() if hist is not None else None)
 
+    def solve_stats(self):
+        """{'host_syncs': stream synchronisations of the last solve's cycle loop, 'coarse_defect': max |A_L Ainv - I|}"""
+        syncs, defect = ctypes.c_int64(), ctypes.c_double()
+        check(self._L.omg_solve_stats(self._h, ctypes.byref(syncs), ctypes.byref(defect)))
+        return {"host_syncs": syncs.value, "coarse_defect": defect.value}
+
     def cycle(self, b, x0=None, level=0, pre=1, post=0, smoother="rbgs", omega=0.8):
         """One mgCycle entered at `level` (openmg/__init__.py:151-236). Returns (uOut, norm)."""
         n = self.n(level)

@@ -147,6 +147,40 @@ def test_thresh_stop_and_cycle_stop(gold_cycles):
         np.testing.assert_allclose(x, z["mgsolve/%d_%d_%d_%g/x" % (N, gl, cycles, thr)], rtol=1e-9, atol=1e-12)
 
 
+def test_threshold_stop_runs_on_the_device():
+    """A thresholded solve tests its stop rule on the device (every cycle sits behind an IF node of its CUDA graph):
+    same cycle count, final norm, history and iterate as the oracle's mgSolve loop, with fewer host
+    synchronisations than cycles; the direct-launch path (one read-back per cycle) agrees bit for bit."""
+    from openmg_b200 import _lib
+    from openmg_b200.hierarchy import Hierarchy
+    for shape, gl, smoother, thr in (((32, 32, 32), 2, "jacobi", 1e-7), ((64, 64), 2, "rbgs", 2e-2),
+                                     ((4096,), 5, "jacobi", 1e-9)):
+        s1 = len(shape) == 1
+        A_in = orc.poisson_csr(shape, sparse_1d=s1)
+        _, b = seeded_problem(A_in)
+        params = {'problemShape': shape, 'gridLevels': gl, 'cycles': 60, 'threshold': thr, 'preIterations': 1,
+                  'postIterations': 1, 'smoother': smoother, 'giveInfo': True}
+        xo, io = orc.mgSolve(A_in, b, dict(params))
+        assert 4 < io['cycle'] < 60, io['cycle']            # the threshold, not the cap, ends the loop
+        h = Hierarchy(A_in, shape, gl - 1, 8)
+        x, cyc, norm, hist = h.solve(b, None, 1, 1, smoother, 0.8, 60, thr, want_history=True)
+        stats = h.solve_stats()
+        assert cyc == io['cycle'] and len(hist) == cyc
+        assert np.isclose(norm, io['norm'], rtol=1e-7) and norm < thr <= hist[-2]
+        np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-12)
+        assert stats['host_syncs'] < cyc, stats
+        # the cycle cap also lives on the device: same history, stops at 3
+        x3, cyc3, norm3, hist3 = h.solve(b, None, 1, 1, smoother, 0.8, 3, thr, want_history=True)
+        assert cyc3 == 3 and np.array_equal(hist3, hist[:3])
+        h.close()
+        h2 = Hierarchy(A_in, shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+        x2, cyc2, norm2, hist2 = h2.solve(b, None, 1, 1, smoother, 0.8, 60, thr, want_history=True)
+        assert cyc2 == cyc and h2.solve_stats()['host_syncs'] == cyc
+        np.testing.assert_array_equal(x2, x)
+        np.testing.assert_array_equal(hist2, hist)
+        h2.close()
+
+
 def test_error_behaviour():
     with pytest.raises(ValueError):
         operators.poisson((1, 2, 3, 4))                           # openmg/tests.py:533-536
