@@ -273,7 +273,7 @@ def ours(args):
     A = problem(shape, s1)
     N = A.n
     t0 = time.perf_counter()
-    h = Hierarchy(A, shape, gl - 1, 8)
+    h = Hierarchy(A, shape, gl - 1, 8, flags=_lib.FLAG_FORCE_CSR if args.force_csr else 0)
     setup_wall = time.perf_counter() - t0
     nlev = h.nlevels
     sizes = [h.level_info(l)["n"] for l in range(nlev)]
@@ -302,6 +302,12 @@ def ours(args):
     value = N * args.steps / (ms * 1e-3)
     peak, peak_src = peaks()
     Bcyc = algorithmic_bytes_per_cycle(sizes, args.pre, args.post)
+    if args.force_csr:
+        # general-matrix path: every application of a level operator also streams the matrix, 12 B per stored
+        # entry (fp64 value + int32 column) + 12 B per row (row length, a_ii)
+        nnzs = [h.level_info(l)["nnzA"] for l in range(nlev)]
+        for l in range(nlev - 1):
+            Bcyc += (args.pre + 1 + args.post) * (12.0 * nnzs[l] + 12.0 * sizes[l])
 
     def cycle_roofline(ms_k):
         ach = Bcyc / (ms_k / args.steps * 1e-3) / 1e9 / world
@@ -386,6 +392,8 @@ def ours(args):
     cpu = cpu_port_rate(base_shape, base_gl, args.pre, args.post, args.smoother,
                         budget_s=20.0 if world == 1 else 8.0)
     cfg = workload_config(shape, gl, args.pre, args.post)
+    if args.force_csr:
+        cfg["workload"] += "; general-matrix path (every level an explicit CSR operator in sliced-ELLPACK form)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -430,6 +438,8 @@ def main():
     ap.add_argument("--smoother", default=None, choices=["jacobi", "rbgs"])
     ap.add_argument("--reps", type=int, default=5, help="repetitions of the K timed cycles (best is reported)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-smoother and strong-scaling legs")
+    ap.add_argument("--force-csr", action="store_true",
+                    help="run the general-matrix path: every level as explicit CSR (no band fast path)")
     ap.add_argument("--pre", type=int, default=1)
     ap.add_argument("--post", type=int, default=1)
     ap.add_argument("--e2e-cycles", type=int, default=10)

@@ -20,6 +20,7 @@ from . import tools
 from . import operators
 from . import solvers
 from .hierarchy import Hierarchy, Operator, BandMatrix
+from . import dist as _dist
 
 tools.poisson = operators.poisson          # north-star alias
 
@@ -110,6 +111,11 @@ def mgSolve(A_in, b, parameters):
 
     if verbose:
         print("Generating restriction matrices; dense=%s" % dense)
+    # under torchrun (one process per GPU, torch.distributed initialised) the fine levels are row slabs across the
+    # ranks: every rank passes the same global b, uploads only the rows it owns, and gets the full x back
+    dist = _dist.active()
+    if dist is not None:
+        _dist.init_from_torch(dist)
     h = parameters.get('hierarchy', None)
     if h is None:
         h = Hierarchy(A_in, problemShape, parameters['coarsestLevel'], parameters['minSize'])
@@ -133,6 +139,8 @@ def mgSolve(A_in, b, parameters):
         if verbose and threshold <= 0 and cycles <= 0:
             _verbose_cycle_trace(nR)
         raise
+    if dist is not None and h.local_range(0)[2]:
+        result = _dist.gather_solution(dist, h, result)
     if verbose:
         for c in range(1, cycle + 1):
             _verbose_cycle_trace(nR)

@@ -508,11 +508,16 @@ static int exec_gated_cycle(omg_hierarchy *h, CycleCfg cfg) {
         CachedGraph cg;
         e = cudaGraphInstantiate(&cg.exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "gated graph instantiate failed: %s", cudaGetErrorString(e));
         cg.cur0_after = h->cur0;
         cg.launches = h->launches - l0 + 2;
         h->launches = l0;
         h->cur0 = cfg.cur0;
+        if (e != cudaSuccess) {
+            // the body holds something a conditional node may not contain (e.g. a captured NCCL collective)
+            cudaGetLastError();
+            h->no_gate = true;
+            return OMG_EUNSUPPORTED;
+        }
         it = h->gated.insert({cfg, cg}).first;
     }
     CUDA_TRY(cudaGraphLaunch(it->second.exec, g.stream));
@@ -621,9 +626,14 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
     // do at least one cycle (openmg/__init__.py:112)
     bool both_disabled = (threshold <= 0.0 && cycles <= 0);
     h->host_syncs = 0;
-    if (every && !(h->flags & OMG_FLAG_NO_GRAPH)) {
-        // a norm after every cycle (threshold stop, or a residual history was asked for): stop test on the device
-        OMG_TRY(solve_gated(h, cfg, cycles, threshold, &cycle, &norm, norm_hist, hist_cap));
+    // a norm after every cycle (threshold stop, or a residual history was asked for): stop test on the device.  Not on
+    // sharded hierarchies: the collectives NCCL captures cannot sit inside a conditional graph node, so there the
+    // host reads the (all-reduced) norm back after every cycle as before.
+    int grc = OMG_EUNSUPPORTED;
+    if (every && !(h->flags & OMG_FLAG_NO_GRAPH) && !h->no_gate && h->first_replicated == 0)
+        grc = solve_gated(h, cfg, cycles, threshold, &cycle, &norm, norm_hist, hist_cap);
+    if (grc != OMG_OK && grc != OMG_EUNSUPPORTED) return grc;      // unsupported: nothing was launched yet
+    if (grc == OMG_OK) {
         if (cycles_done) *cycles_done = cycle;
         if (final_norm) *final_norm = norm;
         if (both_disabled)      // ValueError raised after the first cycle (:118-119)

@@ -47,6 +47,18 @@ struct CsrOp {
     const double *diag;      // a_ii per row
 };
 
+// Sliced ELLPACK view of a CSR level (slices of 32 rows, entries stored column-major in PAIRS): entry k of row i
+// sits at off[i >> 5] + (k >> 1) * 64 + (i & 31) * 2 + (k & 1), so a thread reads its row with one 128-bit value
+// load and one 64-bit column load per two entries and a warp's loads are contiguous 512 B / 256 B segments.
+// Rows keep their CSR entry order (bit-identical sums); slots beyond a row's length are never read.
+struct SellOp {
+    const int *off;          // per slice: first entry (even)
+    const int *rlen;         // per row: entries
+    const int *col;
+    const double *val;
+    const double *diag;
+};
+
 // closed-form restriction for regular shapes (all dims even, C-order strides
 // equal to the reference's NX / NX*NY offsets).  Dims padded to 3 with leading 1s.
 struct RegR {

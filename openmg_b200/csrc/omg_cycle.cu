@@ -29,6 +29,9 @@
         } else if ((L).kind == OMG_KIND_BAND_EXC) {          \
             BandA<1> A{(L).band, (L).exc_op()};              \
             __VA_ARGS__;                                     \
+        } else if ((L).sell_val) {                           \
+            SellA A{(L).sell_op()};                          \
+            __VA_ARGS__;                                     \
         } else {                                             \
             CsrA A{(L).csr_op()};                            \
             __VA_ARGS__;                                     \
@@ -43,7 +46,7 @@ static inline T *V(const Level &L, T *p) { return p - L.row0; }
 int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y) {
     dist_halo_exchange(h, L, x);
     dist_halo_wait(h);
-    ProfScope ps(h, "matvec", lvl(h, L), 16.0 * L.nloc);
+    ProfScope ps(h, "matvec", lvl(h, L), 16.0 * L.nloc + L.matrix_bytes());
     int lo = L.row0, hi = L.row0 + L.nloc;
     DISPATCH_A(L, (k_matvec<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, y))));
     h->launches++;
@@ -53,7 +56,7 @@ int launch_matvec(omg_hierarchy *h, Level &L, double *x, double *y) {
 int launch_residual(omg_hierarchy *h, Level &L, double *x, const double *b, double *r) {
     dist_halo_exchange(h, L, x);
     dist_halo_wait(h);
-    ProfScope ps(h, "residual", lvl(h, L), 24.0 * L.nloc);
+    ProfScope ps(h, "residual", lvl(h, L), 24.0 * L.nloc + L.matrix_bytes());
     int lo = L.row0, hi = L.row0 + L.nloc;
     DISPATCH_A(L, (k_residual<decltype(A)><<<GRID(L.nloc)>>>(A, lo, hi, V(L, x), V(L, b), V(L, r))));
     h->launches++;
@@ -66,7 +69,7 @@ int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int 
     dist_halo_wait(h);
     int blocks = std::min(h->npartial, cdiv(L.nloc, OMG_TPB));
     blocks = std::max(blocks, 1);
-    ProfScope ps(h, "residual_norm", lvl(h, L), 16.0 * L.nloc);
+    ProfScope ps(h, "residual_norm", lvl(h, L), 16.0 * L.nloc + L.matrix_bytes());
     int lo = L.row0, hi = L.row0 + L.nloc;
     DISPATCH_A(L, (k_resnorm_partial<decltype(A)><<<blocks, OMG_TPB, 0, g.stream>>>(A, lo, hi, V(L, x), V(L, b), h->partial)));
     k_final_sum<<<1, 1024, 0, g.stream>>>(h->partial, blocks, h->norm2_dev + slot);
@@ -92,7 +95,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 cur = L.xa;
             } else {
                 dist_halo_exchange(h, L, cur);
-                ProfScope ps(h, "jacobi", lvl(h, L), 24.0 * n);
+                ProfScope ps(h, "jacobi", lvl(h, L), 24.0 * n + L.matrix_bytes());
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_jacobi(h, L, cur, b, out, omega)) {
                 } else {
@@ -116,7 +119,7 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
             }
             for (int c = 0; c < 2; ++c) {
                 dist_halo_exchange(h, L, cur);
-                ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n);
+                ProfScope ps(h, "rbgs_half", lvl(h, L), 12.0 * n + 0.5 * L.matrix_bytes());
                 double *out = other(L, cur);
                 if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_colour_relax(h, L, c, cur, b, out)) {
                 } else {
@@ -145,7 +148,7 @@ int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b
     dist_halo_exchange(h, L, x);
     double *rcv = V(C, rc);                    // indexable by global coarse row
     if (L.regular) {
-        ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n);
+        ProfScope ps(h, "residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n + L.matrix_bytes());
         if (!(h->flags & OMG_FLAG_NO_FUSED) && stencil_residual_restrict(h, L, C, x, b, rcv)) {
         } else {
             dist_halo_wait(h);
@@ -219,7 +222,7 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
         cur = out;
         {   // colour-1 half of that sweep
             dist_halo_exchange(h, L, cur);
-            ProfScope ps(h, "rbgs_half", l, 12.0 * L.nloc);
+            ProfScope ps(h, "rbgs_half", l, 12.0 * L.nloc + 0.5 * L.matrix_bytes());
             out = other(L, cur);
             int lo = L.row0, hi = L.row0 + L.nloc;
             if (!stencil_colour_relax(h, L, 1, cur, b, out)) {

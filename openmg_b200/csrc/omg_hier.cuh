@@ -54,6 +54,11 @@ struct Level {
     int *ptr = nullptr, *col = nullptr;
     double *val = nullptr, *diag = nullptr;
 
+    // sliced-ELLPACK copy of the CSR (CSR-kind levels: the operator the kernels read)
+    int *sell_off = nullptr, *sell_rlen = nullptr, *sell_col = nullptr;
+    double *sell_val = nullptr;
+    int64_t sell_entries = 0;
+
     // restriction to level+1
     bool hasR = false;
     bool regular = false;
@@ -71,6 +76,13 @@ struct Level {
 
     ExcOp exc_op() const { return ExcOp{exc_mask, exc_wpre, exc_ptr, exc_col, exc_val, exc_diag}; }
     CsrOp csr_op() const { return CsrOp{ptr, col, val, diag}; }
+    SellOp sell_op() const { return SellOp{sell_off, sell_rlen, sell_col, sell_val, diag}; }
+    // matrix bytes one application of a CSR-kind operator moves (12 B per stored slot + row length + a_ii);
+    // band levels carry their operator in kernel parameters: 0
+    double matrix_bytes() const {
+        if (kind != OMG_KIND_CSR) return 0.0;
+        return sell_val ? 12.0 * (double)sell_entries + 12.0 * n : 12.0 * (double)nnz + 16.0 * n;
+    }
 };
 
 struct CycleCfg {
@@ -145,6 +157,7 @@ struct omg_hierarchy {
     double *hist_dev = nullptr;
     int hist_dev_cap = 0;
     int64_t host_syncs = 0;          // stream synchronisations issued by the last omg_solve (diagnostic)
+    bool no_gate = false;            // a gated graph could not be instantiated: stop test stays on the host
     int64_t launches = 0;            // kernels launched since last reset
     // timings
     double t_upload_ms = 0, t_galerkin_ms = 0, t_coarse_ms = 0;

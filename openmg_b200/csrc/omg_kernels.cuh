@@ -59,6 +59,27 @@ struct CsrA {
     __device__ __forceinline__ double dg(int i) const { return __ldg(c.diag + i); }
 };
 
+// the vectorised path of CSR levels / general input matrices (openmg/operators.py:172-186): see SellOp
+struct SellA {
+    SellOp c;
+    __device__ __forceinline__ double ax(int i, const double *x, double &d) const {
+        const int len = __ldg(c.rlen + i);
+        const int base = (__ldg(c.off + (i >> 5)) >> 1) + (i & 31);      // in pairs
+        const double2 *v2 = reinterpret_cast<const double2 *>(c.val) + base;
+        const int2 *c2 = reinterpret_cast<const int2 *>(c.col) + base;
+        double acc = 0.0;
+        for (int k = 0; k < len; k += 2) {
+            const double2 v = __ldg(v2 + (k >> 1) * 32);
+            const int2 j = __ldg(c2 + (k >> 1) * 32);
+            acc += v.x * x[j.x];
+            if (k + 1 < len) acc += v.y * x[j.y];
+        }
+        d = __ldg(c.diag + i);
+        return acc;
+    }
+    __device__ __forceinline__ double dg(int i) const { return __ldg(c.diag + i); }
+};
+
 __device__ __forceinline__ int colour_of(const ColourRule &c, int ig) {
     if (c.flat) return ig & 1;
     int s = ig % c.s2;

@@ -1503,6 +1503,57 @@ static double now_ms(cudaEvent_t a, cudaEvent_t b) {
 }
 
 // Level 0 operator is already in h->lv[0] (band and/or CSR).  Builds everything else.
+// ---- sliced ELLPACK (SellOp) from the sorted CSR of a level
+
+__global__ void k_sell_width(const int *__restrict__ ptr, int n, int *__restrict__ rlen, int *__restrict__ slots) {
+    int i = blockIdx.x * OMG_TPB + threadIdx.x;
+    int len = (i < n) ? ptr[i + 1] - ptr[i] : 0;
+    if (i < n) rlen[i] = len;
+    int w = len;
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((threadIdx.x & 31) == 0 && i < n) slots[i >> 5] = ((w + 1) & ~1) * 32;
+}
+
+__global__ void k_sell_fill(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val,
+                            int n, const int *__restrict__ off, int *__restrict__ scol, double *__restrict__ sval) {
+    int i = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (i >= n) return;
+    int p0 = ptr[i], len = ptr[i + 1] - p0;
+    int base = off[i >> 5] + (i & 31) * 2;
+    for (int k = 0; k < len; ++k) {
+        int t = base + (k >> 1) * 64 + (k & 1);
+        scol[t] = col[p0 + k];
+        sval[t] = val[p0 + k];
+    }
+}
+
+static int build_sell(omg_hierarchy *h, Level &L) {
+    if (L.kind != OMG_KIND_CSR || !L.ptr || L.n < 64 || L.row0 != 0 || L.nloc != L.n || getenv("OMG_NO_SELL"))
+        return OMG_OK;
+    int nsl = cdiv(L.n, 32);
+    int *slots = nullptr;
+    OMG_TRY(h_alloc_t(h, &slots, (size_t)nsl + 1, true));
+    OMG_TRY(h_alloc_t(h, &L.sell_rlen, (size_t)L.n));
+    OMG_TRY(h_alloc_t(h, &L.sell_off, (size_t)nsl + 1, true));
+    k_sell_width<<<cdiv(L.n, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.ptr, L.n, L.sell_rlen, slots);
+    int total = 0;
+    OMG_TRY(exclusive_scan_i32(slots, L.sell_off, nsl, &total, g.stream));
+    h_free(h, slots);
+    if (total <= 0 || (double)total > 2.0 * (double)L.nnz + 64.0 * nsl) {
+        // very uneven row lengths: the padded slices would cost more than they save; keep the scalar CSR walk
+        h_free(h, L.sell_rlen);
+        h_free(h, L.sell_off);
+        L.sell_rlen = L.sell_off = nullptr;
+        return OMG_OK;
+    }
+    OMG_TRY(h_alloc_t(h, &L.sell_col, (size_t)total, true));
+    OMG_TRY(h_alloc_t(h, &L.sell_val, (size_t)total, true));
+    k_sell_fill<<<cdiv(L.n, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.ptr, L.col, L.val, L.n, L.sell_off, L.sell_col, L.sell_val);
+    L.sell_entries = total;
+    CUDA_TRY(cudaGetLastError());
+    return OMG_OK;
+}
+
 int build_hierarchy(omg_hierarchy *h) {
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0);
@@ -1519,6 +1570,7 @@ int build_hierarchy(omg_hierarchy *h) {
         k_extract_diag<<<cdiv(C.n, OMG_TPB), OMG_TPB, 0, g.stream>>>(C.ptr, C.col, C.val, C.n, C.row0, C.diag);
         rc = detect_band(h, C);
     }
+    for (int l = 0; l < h->nlev && rc == OMG_OK; ++l) rc = build_sell(h, h->lv[l]);
     cudaEventRecord(e1, g.stream);
     if (rc == OMG_OK && (h->nlev > 1 || (h->flags & OMG_FLAG_FACTOR))) rc = coarse_factor(h);
     cudaEventRecord(e2, g.stream);

@@ -26,10 +26,31 @@ def partition(level_lead, level_rows, level_regular, nranks, rank, agglomerate_b
     return ld.value, row0, nloc
 
 
+_INITED = None
+
+
+def active():
+    """torch.distributed when this process is one rank of an initialised multi-rank group (torchrun), else None.
+    torch is only imported if the launcher's environment says there is such a group."""
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None
+    try:
+        import torch.distributed as dist
+    except Exception:  # noqa: BLE001
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
 def init_from_torch(dist):
-    """Create the library's NCCL communicator for the ranks of an initialised torch.distributed group."""
-    L = _lib.lib()
+    """Create the library's NCCL communicator for the ranks of an initialised torch.distributed group (once)."""
+    global _INITED
     rank, world = dist.get_rank(), dist.get_world_size()
+    if _INITED == (rank, world):
+        return rank, world
+    L = _lib.lib()
     box = [None]
     if rank == 0:
         buf = ctypes.create_string_buffer(128)
@@ -37,6 +58,7 @@ def init_from_torch(dist):
         box[0] = bytes(buf.raw)
     dist.broadcast_object_list(box, src=0)
     _lib.check(L.omg_dist_init(rank, world, box[0]))
+    _INITED = (rank, world)
     return rank, world
 
 
@@ -61,6 +83,13 @@ def gather_solution(dist, hierarchy, x, level=0):
     if not slab:
         return np.asarray(x)
     world = dist.get_world_size()
+    if dist.get_backend() == "nccl":
+        # slabs are equal-sized and ordered by rank (omg_partition): one device all-gather
+        import torch
+        mine = torch.from_numpy(local_slice(x, row0, nloc)).cuda()
+        full = torch.empty(world * nloc, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(full, mine)
+        return full.cpu().numpy()
     meta = [None] * world
     dist.all_gather_object(meta, (row0, nloc))
     return allgather_rows(dist, local_slice(x, row0, nloc), [m[0] for m in meta], [m[1] for m in meta])

@@ -1,5 +1,5 @@
-"""CPU models of the single-pass two-colour sweeps (`k_st2rb` and the experimental `k_st3rb`) and of the
-experimental register-side prolongation (`k_st3e`), openmg_b200/csrc/omg_stencil.cu.
+"""CPU models of the single-pass two-colour sweeps (`k_st2rb` in 2-D / 1-D, `k_rb3` in 3-D),
+openmg_b200/csrc/omg_stencil.cu.
 
 The CUDA kernel relaxes colour 0 of row r from raw rows r-1..r+1 into a "mid" ring and, one row behind,
 colour 1 of row r-1 from mid rows r-2..r, per x-chunk and y-segment, with halo pairs / halo rows recomputed
@@ -163,13 +163,16 @@ def test_corner_rows_couple_through_the_wrapped_pairs():
     assert c2r[2] == Al[N - 1, 0] and c2l[2] == Al[n - N, n - 1]
 
 
-# ------------------------------------------------------------------ 3-D: the register-pipelined variant (k_st3rb)
+# ------------------------------------------------------------------ 3-D: the register-pipelined sweep (k_rb3)
 
 def fused_sweep_model_3d(x, b, S1, NY, NZ, d, c1, cS, cP, TY, ZL, c0=0):
-    """One two-colour sweep the way k_st3rb computes it: full-row chunks of TY rows, z-segments of ZL planes; per
-    item (x-pair of a row) the raw pair of plane p, one raw element of plane p-1, the mid pair of plane p-1 and one
-    mid element of plane p-2 are carried from step to step ("registers"); in-plane neighbours come from the staged
-    raw plane p (pass A) resp. the stored mid plane p-1 (pass B)."""
+    """One two-colour sweep the way k_rb3 computes it: full-row chunks of TY rows, z-segments of ZL planes; pass A
+    relaxes the colour-c0 points of plane p (rows y0-1 .. y0+TY, i.e. including the two recomputed halo rows, which
+    in the first / last chunk are rows of the neighbouring plane with flipped colour parity) from the staged raw
+    planes into the mid plane p; one plane behind, pass B relaxes the other colour of plane p-1 from the mid planes.
+    Centres and z-neighbours are carried from step to step ("registers"), in-plane neighbours come from the staged
+    raw plane p (pass A) resp. the stored mid plane p-1 (pass B).  The kernel groups the x-pairs modelled here into
+    2x2 patches (interior rows) and single pairs (halo rows); the arithmetic per point is the same."""
     S2 = S1 * NY
     n = S2 * NZ
     wod = 1.0 / d

@@ -1,7 +1,8 @@
 """GPU, 2/4/8 ranks (skipped when the box has fewer GPUs): row-slab sharding with the peer-memory halo exchange gives
 the same iterates as the single-GPU (replicated) path and as the oracle.  With 4 and 8 ranks the interior ranks have
 both neighbours; the 1024-wide shape runs the 512-thread kernels of the 8-GPU 1024^3 benchmark line on several slab
-levels."""
+levels.  (3-D shapes need shape[0] == shape[2]: the reference's operators use NX = shape[0] as the row stride,
+openmg/operators.py:244-256, its restriction the C-order strides, openmg/operators.py:63-68.)"""
 import os
 import subprocess
 import sys
@@ -23,7 +24,7 @@ def _ngpus():
 
 
 CASES = [((64, 64, 64), 3, 4096), ((128, 128, 128), 4, 1 << 16), ((256, 256), 4, 1024), ((1024, 1024), 5, 4096),
-         ((65536,), 8, 1024), ((64, 32, 1024), 4, 4096), ((128, 16, 1024), 4, 1 << 14)]
+         ((65536,), 8, 1024), ((512, 16, 512), 4, 1 << 14), ((1024, 16, 1024), 4, 1 << 16)]
 
 
 @pytest.mark.parametrize("nproc", [2, 4, 8])
