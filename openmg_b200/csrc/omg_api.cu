@@ -606,10 +606,14 @@ static int download_x(omg_hierarchy *h, double *x_host) {
     return OMG_OK;
 }
 
-static int check_cfg(int pre, int post, int smoother, double omega) {
+static int check_cfg(const omg_hierarchy *h, int pre, int post, int smoother, double omega) {
     if (pre < 0 || post < 0) return omg_set_error(OMG_EINVAL, "preIterations/postIterations must be >= 0");
     if (smoother < 0 || smoother > 2) return omg_set_error(OMG_EINVAL, "unknown smoother id %d", smoother);
     if (!(omega > 0.0)) return omg_set_error(OMG_EINVAL, "omega must be > 0");
+    // the reference's lexicographic sweep is one sequential chain over all rows: it cannot run on row slabs
+    if (smoother == OMG_SMOOTH_LEXGS && h->first_replicated > 0)
+        return omg_set_error(OMG_EUNSUPPORTED, "smoother 'gs' (lexicographic Gauss-Seidel) is sequential and not "
+                             "available on a hierarchy sharded across GPUs; use 'rbgs' or 'jacobi'");
     return OMG_OK;
 }
 
@@ -617,7 +621,7 @@ int omg_solve(omg_hierarchy *h, const double *b_host, double *x_host, int has_in
               int smoother, double omega, int cycles, double threshold, int *cycles_done, double *final_norm,
               double *norm_hist, int hist_cap) {
     CHECK_H(h);
-    OMG_TRY(check_cfg(pre, post, smoother, omega));
+    OMG_TRY(check_cfg(h, pre, post, smoother, omega));
     OMG_TRY(upload_state(h, b_host, x_host, has_initial));
     bool every = (threshold > 0.0) || (norm_hist != nullptr && hist_cap > 0);
     CycleCfg cfg{pre, post, smoother, 0, omega, 0};
@@ -675,7 +679,7 @@ int omg_solve_stats(const omg_hierarchy *h, int64_t *host_syncs, double *coarse_
 int omg_cycle(omg_hierarchy *h, int level, const double *b_host, double *x_host, int has_initial, int pre,
               int post, int smoother, double omega, double *norm) {
     CHECK_LEVEL(h, level);
-    OMG_TRY(check_cfg(pre, post, smoother, omega));
+    OMG_TRY(check_cfg(h, pre, post, smoother, omega));
     double nv = 0;
     if (level == 0) {
         OMG_TRY(upload_state(h, b_host, x_host, has_initial));
@@ -711,7 +715,7 @@ int omg_set_rhs(omg_hierarchy *h, const double *b_host) {
 int omg_bench_cycles(omg_hierarchy *h, int pre, int post, int smoother, double omega, int ncycles, int with_norm,
                      float *ms, int64_t *launches) {
     CHECK_H(h);
-    OMG_TRY(check_cfg(pre, post, smoother, omega));
+    OMG_TRY(check_cfg(h, pre, post, smoother, omega));
     if (ncycles <= 0) return omg_set_error(OMG_EINVAL, "ncycles must be > 0");
     CycleCfg cfg{pre, post, smoother, with_norm ? 1 : 0, omega, 0};
     // make sure both ping-pong parities are captured outside the timed region
@@ -745,7 +749,7 @@ int omg_bench_cycles(omg_hierarchy *h, int pre, int post, int smoother, double o
 int omg_profile_cycle(omg_hierarchy *h, int pre, int post, int smoother, double omega, int reps, char *json,
                       int cap) {
     CHECK_H(h);
-    OMG_TRY(check_cfg(pre, post, smoother, omega));
+    OMG_TRY(check_cfg(h, pre, post, smoother, omega));
     if (reps <= 0 || !json || cap < 64) return omg_set_error(OMG_EINVAL, "bad arguments to omg_profile_cycle");
     CycleCfg cfg{pre, post, smoother, 0, omega, 0};
     OMG_TRY(upload_state(h, nullptr, nullptr, 0));
@@ -819,7 +823,7 @@ int omg_current_norm(omg_hierarchy *h, double *norm) {
 int omg_smooth(omg_hierarchy *h, int level, const double *b_host, double *x_host, int sweeps, int smoother,
                double omega) {
     CHECK_LEVEL(h, level);
-    OMG_TRY(check_cfg(sweeps, 0, smoother, omega));
+    OMG_TRY(check_cfg(h, sweeps, 0, smoother, omega));
     Level &L = h->lv[level];
     OMG_TRY(up(L, L.b, b_host));
     OMG_TRY(up(L, L.xa, x_host));
@@ -855,7 +859,7 @@ int omg_prolong_correct_smooth(omg_hierarchy *h, int level, const double *b_host
                                double *x_host, int sweeps, int smoother, double omega) {
     CHECK_LEVEL(h, level);
     if (level >= h->nlev - 1) return omg_set_error(OMG_EINVAL, "level %d has no restriction", level);
-    OMG_TRY(check_cfg(sweeps, 0, smoother, omega));
+    OMG_TRY(check_cfg(h, sweeps, 0, smoother, omega));
     Level &L = h->lv[level];
     Level &C = h->lv[level + 1];
     OMG_TRY(up(C, C.xa, ec_host));
@@ -869,7 +873,7 @@ int omg_prolong_correct_smooth(omg_hierarchy *h, int level, const double *b_host
 int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, double *x_host, double threshold,
                             int max_sweeps, int smoother, double omega, int *sweeps_done, double *norm) {
     CHECK_LEVEL(h, level);
-    OMG_TRY(check_cfg(0, 0, smoother, omega));
+    OMG_TRY(check_cfg(h, 0, 0, smoother, omega));
     Level &L = h->lv[level];
     OMG_TRY(up(L, L.b, b_host));
     OMG_TRY(up(L, L.xa, x_host));

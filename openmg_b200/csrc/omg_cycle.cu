@@ -112,10 +112,11 @@ double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, in
                 // both colours in one pass (unsharded pure-band levels)
                 ProfScope ps(h, "rbgs_sweep", lvl(h, L), 24.0 * n);
                 double *out = other(L, cur);
-                stencil_rb_sweep(h, L, cur, b, out);
-                cur = out;
-                h->launches++;
-                continue;
+                if (stencil_rb_sweep(h, L, cur, b, out)) {
+                    cur = out;
+                    h->launches++;
+                    continue;
+                }
             }
             for (int c = 0; c < 2; ++c) {
                 dist_halo_exchange(h, L, cur);
@@ -190,23 +191,34 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
         if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
         dist_halo_exchange(h, C, e);
         double *out = other(L, cur);
+        bool ok;
         {
             ProfScope ps(h, "prolong_jacobi", l, 24.0 * L.nloc + 8.0 * L.piece_n);
-            stencil_prolong_jacobi(h, L, C, cur, e, b, out, omega);
+            ok = stencil_prolong_jacobi(h, L, C, cur, e, b, out, omega);
         }
-        h->launches++;
-        return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+        if (ok) {
+            h->launches++;
+            return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+        }
+        dist_halo_wait(h);          // launch failed after a successful probe: unfused path below
+        launch_prolong_correct(h, l, e, cur, cur);
+        return launch_smooth(h, L, smoother, omega, sweeps, cur, b);
     }
     if (sweeps > 0 && smoother == OMG_SMOOTH_RBGS && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
         stencil_prolong_rb_sweep(h, L, C, nullptr, nullptr, nullptr, nullptr)) {          // applicability probe
         // correction fused with the whole first post-smoothing sweep
         double *out = other(L, cur);
+        bool ok;
         {
             ProfScope ps(h, "prolong_rbgs_sweep", l, 24.0 * L.nloc + 8.0 * L.piece_n);
-            stencil_prolong_rb_sweep(h, L, C, cur, e, b, out);
+            ok = stencil_prolong_rb_sweep(h, L, C, cur, e, b, out);
         }
-        h->launches++;
-        return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+        if (ok) {
+            h->launches++;
+            return launch_smooth(h, L, smoother, omega, sweeps - 1, out, b);
+        }
+        launch_prolong_correct(h, l, e, cur, cur);
+        return launch_smooth(h, L, smoother, omega, sweeps, cur, b);
     }
     if (sweeps > 0 && smoother == OMG_SMOOTH_RBGS && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
         stencil_prolong_colour_relax(h, L, C, 0, nullptr, nullptr, nullptr, nullptr)) {   // applicability probe
@@ -214,9 +226,15 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
         if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
         dist_halo_exchange(h, C, e);
         double *out = other(L, cur);
+        bool ok;
         {
             ProfScope ps(h, "prolong_rbgs_half", l, 12.0 * L.nloc + 8.0 * L.piece_n);
-            stencil_prolong_colour_relax(h, L, C, 0, cur, e, b, out);
+            ok = stencil_prolong_colour_relax(h, L, C, 0, cur, e, b, out);
+        }
+        if (!ok) {
+            dist_halo_wait(h);
+            launch_prolong_correct(h, l, e, cur, cur);
+            return launch_smooth(h, L, smoother, omega, sweeps, cur, b);
         }
         h->launches++;
         cur = out;
@@ -265,9 +283,13 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
             ProfScope ps(h, "jacobi0_residual_restrict", l, 16.0 * L.nloc + 8.0 * L.piece_n);
             fused0 = stencil_jacobi0_residual_restrict(h, L, C, L.b, L.xa, V(C, C.b), cfg.omega);
         }
-        cur = L.xa;
-        h->launches++;
-        if (L.slab && !C.slab) dist_allgather(h, V(C, C.b) + L.piece_row0, V(C, C.b), (size_t)L.piece_n);
+        if (fused0) {
+            cur = L.xa;
+            h->launches++;
+            if (L.slab && !C.slab) dist_allgather(h, V(C, C.b) + L.piece_row0, V(C, C.b), (size_t)L.piece_n);
+        } else {
+            dist_halo_wait(h);      // the real launch failed after a successful probe: generic path from the zero iterate
+        }
     }
     if (!fused0) {
         cur = launch_smooth(h, L, cfg.smoother, cfg.omega, cfg.pre, cur, L.b);

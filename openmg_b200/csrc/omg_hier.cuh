@@ -44,6 +44,7 @@ struct Level {
     int *exc_crows = nullptr;    // coarse rows whose aggregate contains an exception row (regular R)
     int nexc_crows = 0;
     bool exc_diag_uniform = true; // every exception row has a_ii == band.diag
+    int exc_reach = 0;            // max |column - row| over the exception rows
     bool classed = false;         // all exception rows follow the 9 positional stencil classes below
     ClsTab cls{};
     bool classed2 = false;        // 2-D analogue: rows of the first / last grid column carry three correction taps each

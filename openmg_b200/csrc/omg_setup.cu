@@ -661,6 +661,17 @@ __global__ void __launch_bounds__(OMG_TPB) k_exc_fill(const int *__restrict__ ro
     ediag[s] = d;
 }
 
+// max |column - row| over the exception rows: a slab level exchanges halos sized from the BAND reach, so exception
+// rows reaching further (possible when the level comes from a general input matrix) rule out sharding it
+__global__ void k_exc_reach(const int *__restrict__ rows, int nexc, const int *__restrict__ eptr,
+                            const int *__restrict__ ecol, int *__restrict__ reach) {
+    int s = blockIdx.x * OMG_TPB + threadIdx.x;
+    if (s >= nexc) return;
+    int i = rows[s], m = 0;
+    for (int p = eptr[s]; p < eptr[s + 1]; ++p) m = max(m, abs(ecol[p] - i));
+    atomicMax(reach, m);
+}
+
 // global coarse row of every exception row -> bit mask over coarse rows (global index - 0 on one GPU)
 __global__ void k_mark_crows(const int *__restrict__ rows, int nexc, RegR R, int frow0, unsigned *__restrict__ cmask) {
     int s = blockIdx.x * OMG_TPB + threadIdx.x;
@@ -970,13 +981,16 @@ static int detect_band(omg_hierarchy *h, Level &L) {
     k_exc_fill<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(rows, nexc, L.ptr, L.col, L.val, eptr, L.row0,
                                                               L.exc_col, L.exc_val, L.exc_diag);
     {   // are all exception diagonals equal to the stencil diagonal? (true for the Poisson hierarchies)
+        // and how far do the exception rows reach?
         int *flag = nullptr;
-        OMG_TRY(h_alloc_t(h, &flag, 1, true));
+        OMG_TRY(h_alloc_t(h, &flag, 2, true));
         k_diag_differs<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(L.exc_diag, nexc, band.diag, flag);
-        int f = 0;
-        CUDA_TRY(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        k_exc_reach<<<cdiv(nexc, OMG_TPB), OMG_TPB, 0, g.stream>>>(rows, nexc, eptr, L.exc_col, flag + 1);
+        int f[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(f, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
         CUDA_TRY(cudaStreamSynchronize(g.stream));
-        L.exc_diag_uniform = (f == 0);
+        L.exc_diag_uniform = (f[0] == 0);
+        L.exc_reach = f[1];
         h_free(h, flag);
     }
     L.exc_rows = rows;
@@ -1430,8 +1444,10 @@ static int alloc_vectors(omg_hierarchy *h) {
         Level &L = h->lv[l];
         lead[l] = L.shape[0];
         rows[l] = L.n;
-        // a slab level needs the closed-form restriction and a band operator (halo = band reach)
+        // a slab level needs the closed-form restriction and a band operator (halo = band reach) whose exception
+        // rows, if any, stay inside that reach
         regular[l] = (L.hasR && L.regular && L.kind != OMG_KIND_CSR) ? 1 : 0;
+        if (L.kind == OMG_KIND_BAND_EXC && L.exc_reach > ((reach[l] + reach2[l] + 1) & ~1)) regular[l] = 0;
     }
     const char *env = getenv("OMG_AGGLOMERATE_BELOW");
     int64_t agg_below = env ? atoll(env) : (1ll << 19);
