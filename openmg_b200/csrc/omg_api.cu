@@ -6,6 +6,10 @@
 
 #include <algorithm>
 
+#include <ctype.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "omg_hier.cuh"
 
 Globals g;
@@ -93,9 +97,52 @@ int omg_device_info(char *buf, int buflen, int *sm_count, int64_t *mem_bytes) {
     return OMG_OK;
 }
 
+// NUMA placement of pinned host buffers.  cudaMallocHost pins the pages where the calling thread's memory policy
+// puts them — by default all on the node the process happens to run on, so with one process per GPU the eight
+// ranks' host<->device copies all hammer the same memory controllers.  Place the buffer on the NUMA node the GPU
+// hangs off (/sys/bus/pci/devices/<bdf>/numa_node) when that is known, else interleave it over all nodes.
+// Raw syscalls (no libnuma in the image); any failure leaves the default policy in place.
+static int gpu_numa_node() {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, g.device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+static int numa_node_count() {
+    int n = 0;
+    for (; n < 64; ++n) {
+        char path[64];
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d", n);
+        if (access(path, F_OK) != 0) break;
+    }
+    return n;
+}
+
 int omg_host_alloc(void **ptr, int64_t bytes) {
     if (!g.inited) return omg_set_error(OMG_ENODEV, "omg_init() has not succeeded");
-    CUDA_TRY(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 16)));
+    const int MPOL_DEFAULT_ = 0, MPOL_PREFERRED_ = 1, MPOL_INTERLEAVE_ = 3;
+    bool policy_set = false;
+    if (!getenv("OMG_NO_NUMA")) {
+        int nodes = numa_node_count(), node = gpu_numa_node();
+        if (nodes > 1) {
+            unsigned long mask = (node >= 0 && node < nodes) ? (1ul << node) : ((1ul << nodes) - 1ul);
+            int mode = (node >= 0 && node < nodes) ? MPOL_PREFERRED_ : MPOL_INTERLEAVE_;
+            policy_set = syscall(SYS_set_mempolicy, mode, &mask, (unsigned long)(8 * sizeof mask)) == 0;
+        }
+    }
+    cudaError_t e = cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 16));
+    if (policy_set) syscall(SYS_set_mempolicy, MPOL_DEFAULT_, nullptr, 0ul);
+    if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "cudaMallocHost failed: %s", cudaGetErrorString(e));
     return OMG_OK;
 }
 int omg_host_free(void *ptr) {

@@ -83,6 +83,16 @@ int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int 
 double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, int sweeps, double *cur,
                       const double *b) {
     int n = L.nloc, lo = L.row0, hi = L.row0 + L.nloc;
+    if (cur == nullptr && sweeps > 0 && smoother == OMG_SMOOTH_RBGS && !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_rb_sweep0(h, L, nullptr, nullptr)) {
+        // zero initial iterate (openmg/__init__.py:191-192): the first two-colour sweep reads only b
+        ProfScope ps(h, "rbgs_sweep0", lvl(h, L), 16.0 * n);
+        if (stencil_rb_sweep0(h, L, b, L.xa)) {
+            cur = L.xa;
+            h->launches++;
+            --sweeps;
+        }
+    }
     if (cur == nullptr && (sweeps == 0 || smoother != OMG_SMOOTH_JACOBI)) {
         cudaMemsetAsync(L.xa, 0, sizeof(double) * (size_t)n, g.stream);
         cur = L.xa;

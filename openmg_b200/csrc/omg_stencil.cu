@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
             int qq = q + 1;
             mbar_wait(full + (qq % NS), (uint32_t)((qq / NS) & 1));
             if (XF) {
+                // (transforming one plane further ahead, so that the closing barrier of the previous step publishes
+                // it and this barrier goes away, was measured SLOWER: 0.65 vs 0.57 ms at 512^3 — with four planes
+                // resident the ring has no stage left in flight)
                 transform(qq % NS, z + 1);
                 if (z + 2 <= z1) load_aux(z + 2);
                 __syncthreads();
@@ -1684,6 +1687,8 @@ __device__ __forceinline__ double rb3_corr(const ClsTab &T, int cls, const doubl
     return a;
 }
 
+// MODE 0: one sweep on xi.  MODE 2: y = xi + R^T e, then one sweep on y.  MODE 3: one sweep from the ZERO iterate
+// (openmg/__init__.py:191-192: coarse levels start from zeros): xi is b, x is neither read nor cleared beforehand.
 template <int MODE, bool CLS>
 __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1846,7 +1851,19 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
                 rb[k] = lds2(rawc + ro + k * KS + S1);
             }
         }
-        if (relax) {
+        double g3a[RB3_PPT], g3b[RB3_PPT];     // MODE 3: b of plane p at the positions pass B(p) relaxes
+        if (MODE == 3) {
+            // ---- pass A from the zero iterate (the staged planes hold b): every coupling multiplies a zero, so the
+            // colour-c0 points become b/a_ii and everything else stays zero — no neighbour is read
+#pragma unroll
+            for (int k = 0; k < RB3_PPT; ++k) {
+                g3a[k] = el(ra[k], 1 - EA);
+                g3b[k] = el(rb[k], 1 - EB);
+                const double nva = P.wod * el(ra[k], EA), nvb = P.wod * el(rb[k], EB);
+                ra[k] = EA ? make_double2(0.0, nva) : make_double2(nva, 0.0);
+                rb[k] = EB ? make_double2(0.0, nvb) : make_double2(nvb, 0.0);
+            }
+        } else if (relax) {
             // ---- pass A
 #pragma unroll
             for (int k = 0; k < RB3_PPT; ++k) {
@@ -1898,7 +1915,10 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
             double2 hr = make_double2(0.0, 0.0);
             if (has_cur) hr = lds2(rawc + ho);
             double2 hm = hr;
-            if (real && p + hshift >= 0 && p + hshift < P.NZ) {
+            if (MODE == 3) {
+                const double nv = P.wod * (he ? hr.y : hr.x);
+                hm = he ? make_double2(0.0, nv) : make_double2(nv, 0.0);
+            } else if (real && p + hshift >= 0 && p + hshift < P.NZ) {
                 const double c = he ? hr.y : hr.x;
                 const double xl = he ? hr.x : rawc[ho - 1];
                 const double xr = he ? rawc[ho + 2] : hr.y;
@@ -1914,7 +1934,7 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
             }
             if (real) sts2(midw + ho, hm);
             hzm = he ? hr.x : hr.y;          // raw plane p at the position relaxed on plane p+1
-            if (p + 1 >= z0 - 1 && p + 1 <= z1 && p + 1 + hshift >= 0 && p + 1 + hshift < P.NZ)
+            if (MODE != 3 && p + 1 >= z0 - 1 && p + 1 <= z1 && p + 1 + hshift >= 0 && p + 1 + hshift < P.NZ)
                 hb = __ldg(P.b + (long long)(p + 1) * P.S2 + gbase + ho + (1 - he));
         }
         if (CLS && real) __syncthreads();     // the class taps of pass B read mid plane p at other threads' positions
@@ -1968,11 +1988,16 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
                 ub[k] = el(mb[k], 1 - EB);
                 // (opaque moves: if ga/gb merely aliased halves of ba/bb, the b registers could not be reloaded in place
                 // and the loop back-edge would have to move b values that are still in flight)
-                asm volatile("mov.f64 %0, %1;" : "=d"(ga[k]) : "d"(el(ba[k], 1 - EA)));
-                asm volatile("mov.f64 %0, %1;" : "=d"(gb[k]) : "d"(el(bb[k], 1 - EB)));
+                if (MODE == 3) {
+                    ga[k] = g3a[k];
+                    gb[k] = g3b[k];
+                } else {
+                    asm volatile("mov.f64 %0, %1;" : "=d"(ga[k]) : "d"(el(ba[k], 1 - EA)));
+                    asm volatile("mov.f64 %0, %1;" : "=d"(gb[k]) : "d"(el(bb[k], 1 - EB)));
+                }
                 ma[k] = ra[k];
                 mb[k] = rb[k];
-                if (bnext) {
+                if (MODE != 3 && bnext) {
                     ba[k] = ldg2(bpn + o);
                     bb[k] = ldg2(bpn + o + S1);
                 }
@@ -2081,7 +2106,7 @@ static bool rb3_launch(omg_hierarchy *h, const Rb3 &P, bool cls) {
     const int NS = cls ? 4 : 3, NM = cls ? 3 : 2;
     size_t smem = ((size_t)NS * P.RS + (size_t)NM * P.MS) * sizeof(double) + 64;
     void (*kern)(const Rb3) = cls ? k_rb3<MODE, true> : k_rb3<MODE, false>;
-    if (!attr_set[cls]) {
+    if (!attr_set[cls]) {        // (static per MODE instantiation)
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
@@ -2113,6 +2138,18 @@ bool stencil_rb_sweep(omg_hierarchy *h, Level &L, const double *xi, const double
     Q.wod = 1.0 / Q.d;
     Q.colour = 0;
     return st2rb_launch<0>(h, Q);
+}
+
+// one full two-colour sweep from the zero iterate: xo = rbgs(A, b, 0), x is never read.  b == nullptr: probe.
+bool stencil_rb_sweep0(omg_hierarchy *h, Level &L, const double *b, double *xo) {
+    Rb3 T{};
+    bool cls3;
+    if (!rb3_params(L, &T, &cls3, false)) return false;
+    if (!b) return true;
+    T.xi = b;
+    T.b = b;
+    T.xo = xo;
+    return rb3_launch<3>(h, T, cls3);
 }
 
 // y = xi + R^T e, then one full two-colour sweep on y, in a single pass.  xi == nullptr: probe.

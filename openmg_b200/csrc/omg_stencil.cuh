@@ -22,3 +22,5 @@ bool stencil_prolong_colour_relax(omg_hierarchy *h, Level &L, Level &C, int colo
 bool stencil_rb_sweep(omg_hierarchy *h, Level &L, const double *xi, const double *b, double *xo);
 bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *e,
                               const double *b, double *xo);
+// one full two-colour sweep from the zero iterate, x never read (coarse levels of a cycle).  b == nullptr: probe
+bool stencil_rb_sweep0(omg_hierarchy *h, Level &L, const double *b, double *xo);
