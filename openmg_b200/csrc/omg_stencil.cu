@@ -86,6 +86,7 @@ __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_c
 __device__ __forceinline__ void sts2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
+
 // MODE 0: xo = xi + omega (b - A xi)/d
 // MODE 1: rc = R (b - A xi)
 // MODE 2: y = xi + R^T e ; xo = y + omega (b - A y)/d
@@ -130,9 +131,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
         p = act[k] ? p : 0;
         py[k] = p / HX;
         px[k] = p - py[k] * HX;
-        if (CLS && k == 1 && (HX & 63) == 0) {
+        if (CLS && k == 1 && (HX & 63) == 0 && (NT % HX) == 0) {
             // the class corrections run on the lanes px == 0 and px == HX-1 only: rotate the second patch of every
-            // thread by half a row so that each warp owns one of them instead of half the warps owning two
+            // thread by half a row so that each warp owns one of them instead of half the warps owning two.
+            // (Only when a thread's two patches sit in different rows, NT a multiple of HX: with 128 threads on
+            // 512-wide rows — thin slabs of a sharded level — both are in the same row and the rotation would map
+            // the second half of the row onto the first.)
             px[k] += HX >> 1;
             if (px[k] >= HX) px[k] -= HX;
         }
@@ -1095,6 +1099,7 @@ static int env_int(const char *name, int dflt) {
 // Does level L carry a 3-D 7-point constant band this path can run?  Fills geometry + tiling.
 static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     if (L.kind == OMG_KIND_CSR || L.band.nb != 6) return false;
+    if (L.nloc < env_int("OMG_ST_MIN_ROWS", 0)) return false;      // experiment knob: generic kernels on small levels
     const BandOp &B = L.band;
     if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return false;
     if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;

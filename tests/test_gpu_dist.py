@@ -24,7 +24,7 @@ def _ngpus():
 
 
 CASES = [((64, 64, 64), 3, 4096), ((128, 128, 128), 4, 1 << 16), ((256, 256), 4, 1024), ((1024, 1024), 5, 4096),
-         ((65536,), 8, 1024), ((512, 16, 512), 4, 1 << 14), ((1024, 16, 1024), 4, 1 << 16)]
+         ((1 << 18,), 10, 1024), ((512, 16, 512), 4, 1 << 14), ((1024, 16, 1024), 4, 1 << 16)]
 
 
 @pytest.mark.parametrize("nproc", [2, 4, 8])

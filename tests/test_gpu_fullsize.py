@@ -178,3 +178,30 @@ def test_config4_scaled_256_cube_vs_oracle():
         assert rel(x, xo) <= tol, smoother
         np.testing.assert_allclose(hist, norms, rtol=1e-9)
     h.close()
+
+
+def test_thin_slab_tiling_on_class_corrected_wide_rows(monkeypatch):
+    """128-thread CTAs on 512-wide rows of a class-corrected (Galerkin) level: the tiling a thin slab of a sharded
+    level gets (at most 2^19 rows per rank).  A thread's two patches then sit in the SAME row; the half-row rotation
+    of the second patch (a load-balancing trick for the class lanes) must not be applied.  Found at 4 and 8 ranks by
+    tools/dist_check.py; pinned here on one GPU by forcing the tiling."""
+    import scipy.sparse as sp
+    monkeypatch.setenv("OMG_ST_NT", "128")
+    shape, gl = (1024, 16, 1024), 4
+    A0 = orc.poisson_csr(shape)
+    R = orc.restrictionList(shape, 1, 8)[:2]
+    A = orc.coeffecientList(A0, R)
+    h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8)
+    assert h.level_info(1)["kind"] == "band+exc"
+    l = 1
+    Al = sp.csr_matrix(A[l])
+    n = Al.shape[0]
+    rs = np.random.RandomState(29)
+    x, b, e = rs.random_sample(n), rs.random_sample(n), rs.random_sample(R[l].shape[0])
+    y = x + R[l].T.dot(e)
+    col = orc.colouring(shape, l, n)
+    assert rel(h.smooth(l, b, x, 2, "jacobi", 0.8), orc.jacobi(Al, b, x.copy(), 2, 0.8)) <= 1e-12
+    assert rel(h.smooth(l, b, x, 1, "rbgs"), orc.rbgs(Al, b, x.copy(), 1, col)) <= 1e-10
+    assert rel(h.residual_restrict(l, b, x), R[l].dot(b - Al.dot(x))) <= 1e-13
+    assert rel(h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8), orc.jacobi(Al, b, y.copy(), 1, 0.8)) <= 1e-12
+    h.close()
