@@ -644,7 +644,18 @@ static int upload_state(omg_hierarchy *h, const double *b_host, const double *x_
     return OMG_OK;
 }
 
+// a stencil kernel gave up waiting for a neighbour during a fused halo pull: the iterate is invalid
+static int check_pull(omg_hierarchy *h) {
+    bool bad = false;
+    OMG_TRY(dist_pull_timed_out(h, &bad));
+    if (bad)
+        return omg_set_error(OMG_ECUDA, "a fused halo pull timed out waiting for a neighbouring rank (set "
+                                        "OMG_NO_HALO_PULL=1 to exchange halos with separate copies)");
+    return OMG_OK;
+}
+
 static int download_x(omg_hierarchy *h, double *x_host) {
+    if (h->first_replicated > 0) OMG_TRY(check_pull(h));
     Level &L = h->lv[0];
     const double *cur = h->cur0 ? L.xb : L.xa;
     CUDA_TRY(cudaMemcpyAsync(x_host + L.row0, cur, sizeof(double) * (size_t)L.nloc, cudaMemcpyDeviceToHost,
@@ -786,6 +797,7 @@ int omg_bench_cycles(omg_hierarchy *h, int pre, int post, int smoother, double o
     cudaEventDestroy(e1);
     if (rc != OMG_OK) return rc;
     if (e != cudaSuccess) return omg_set_error(OMG_ECUDA, "bench failed: %s", cudaGetErrorString(e));
+    if (h->first_replicated > 0) OMG_TRY(check_pull(h));
     if (ms) *ms = t;
     if (launches) *launches = h->launches - l0;
     return OMG_OK;

@@ -198,7 +198,8 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
     Level &C = h->lv[l + 1];
     if (sweeps > 0 && smoother == OMG_SMOOTH_JACOBI && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
         stencil_prolong_jacobi(h, L, C, nullptr, nullptr, nullptr, nullptr, omega)) {     // applicability probe
-        if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
+        // (a fused pull reads the neighbours' rows inside the kernel and leaves nothing in the local halo rows)
+        if (!cur_halo_valid || h->peer.pull_ok) dist_halo_exchange(h, L, cur);
         dist_halo_exchange(h, C, e);
         double *out = other(L, cur);
         bool ok;
@@ -233,7 +234,7 @@ double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, dou
     if (sweeps > 0 && smoother == OMG_SMOOTH_RBGS && L.regular && !(h->flags & OMG_FLAG_NO_FUSED) &&
         stencil_prolong_colour_relax(h, L, C, 0, nullptr, nullptr, nullptr, nullptr)) {   // applicability probe
         // correction fused with the colour-0 half of the first post-smoothing sweep
-        if (!cur_halo_valid) dist_halo_exchange(h, L, cur);
+        if (!cur_halo_valid || h->peer.pull_ok) dist_halo_exchange(h, L, cur);
         dist_halo_exchange(h, C, e);
         double *out = other(L, cur);
         bool ok;

@@ -316,7 +316,11 @@ int dist_peer_setup(omg_hierarchy *h) {
     CUDA_TRY(cudaMalloc((void **)&P.epochs, sizeof(unsigned long long) * nslot));
     CUDA_TRY(cudaMemset(P.flags, 0, sizeof(unsigned long long) * 4 * nslot));
     CUDA_TRY(cudaMemset(P.epochs, 0, sizeof(unsigned long long) * nslot));
-    int nh = 1 + nslot;
+    CUDA_TRY(cudaMalloc((void **)&P.pull, sizeof(unsigned long long) * 8 * nslot));
+    CUDA_TRY(cudaMemset(P.pull, 0, sizeof(unsigned long long) * 8 * nslot));
+    CUDA_TRY(cudaMalloc((void **)&P.pull_timeout, sizeof(int)));
+    CUDA_TRY(cudaMemset(P.pull_timeout, 0, sizeof(int)));
+    int nh = 2 + nslot;
     std::vector<cudaIpcMemHandle_t> mine(nh), all((size_t)nh * g.nranks);
     CUDA_TRY(cudaIpcGetMemHandle(&mine[0], P.flags));
     for (int l = 0; l < nslab; ++l) {
@@ -324,6 +328,7 @@ int dist_peer_setup(omg_hierarchy *h) {
         CUDA_TRY(cudaIpcGetMemHandle(&mine[2 + 3 * l], h->lv[l].xb_base));
         CUDA_TRY(cudaIpcGetMemHandle(&mine[3 + 3 * l], h->lv[l].b_base));
     }
+    CUDA_TRY(cudaIpcGetMemHandle(&mine[1 + nslot], P.pull));
     OMG_TRY(allgather_bytes(mine.data(), all.data(), sizeof(cudaIpcMemHandle_t) * nh));
     P.base_dn.assign(nslot, nullptr);
     P.base_up.assign(nslot, nullptr);
@@ -340,6 +345,9 @@ int dist_peer_setup(omg_hierarchy *h) {
             P.opened.push_back(p);
             (side == 0 ? P.base_dn : P.base_up)[s] = (double *)p;
         }
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, ph[1 + nslot], cudaIpcMemLazyEnablePeerAccess));
+        P.opened.push_back(p);
+        (side == 0 ? P.pull_dn : P.pull_up) = (unsigned long long *)p;
     }
     // nobody may start signalling before everyone has mapped and zeroed: a barrier over NCCL
     double *tok = nullptr;
@@ -349,6 +357,7 @@ int dist_peer_setup(omg_hierarchy *h) {
     CUDA_TRY(cudaStreamSynchronize(g.stream2));
     cudaFree(tok);
     P.enabled = true;
+    P.pull_ok = getenv("OMG_NO_HALO_PULL") == nullptr;
     return OMG_OK;
 }
 
@@ -358,14 +367,67 @@ void dist_peer_teardown(omg_hierarchy *h) {
     P.opened.clear();
     if (P.flags) cudaFree(P.flags);
     if (P.epochs) cudaFree(P.epochs);
+    if (P.pull) cudaFree(P.pull);
+    if (P.pull_timeout) cudaFree(P.pull_timeout);
+    P.pull = nullptr;
+    P.pull_timeout = nullptr;
+    P.pull_ok = false;
     P.flags = P.epochs = nullptr;
     P.enabled = false;
 }
 
 // Start filling the halos of vector v (owned pointer) of slab level L: hw elements from each
 // neighbour.  Asynchronous: dist_halo_wait() makes the compute stream wait for it.
+static int halo_exchange_now(omg_hierarchy *h, Level &L, double *v);
+
+// With the fused pull available the exchange is only REQUESTED here: a 3-D stencil kernel that consumes the vector
+// reads its boundary planes straight from the neighbours (omg_stencil.cu), any other consumer reaches
+// dist_halo_wait, which issues the pending requests on the comm stream first.
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v) {
     if (g.nranks == 1 || !L.slab) return OMG_OK;
+    if (h->peer.pull_ok && peer_slot(L, 0, v) >= 0) {
+        for (auto &r : h->halo_req)
+            if (r.first == &L && r.second == v) return OMG_OK;
+        h->halo_req.push_back({&L, v});
+        return OMG_OK;
+    }
+    return halo_exchange_now(h, L, v);
+}
+
+int dist_halo_flush(omg_hierarchy *h) {
+    std::vector<std::pair<Level *, double *>> req;
+    req.swap(h->halo_req);
+    for (auto &r : req) OMG_TRY(halo_exchange_now(h, *r.first, r.second));
+    return OMG_OK;
+}
+
+// peer pointers for the in-kernel pull of vector v (owned-row-0 pointer) of slab level L
+bool dist_pull_params(omg_hierarchy *h, Level &L, const double *v, HaloPull *out) {
+    PeerState &P = h->peer;
+    if (!P.pull_ok || !L.slab) return false;
+    int l = (int)(&L - h->lv.data());
+    int slot = peer_slot(L, l, v);
+    if (slot < 0) return false;
+    bool has_dn = g.rank > 0, has_up = g.rank < g.nranks - 1;
+    out->mine = P.pull + 8 * slot;
+    out->peer_dn = has_dn ? P.pull_dn + 8 * slot : nullptr;
+    out->peer_up = has_up ? P.pull_up + 8 * slot : nullptr;
+    out->v_dn = has_dn ? P.base_dn[slot] + L.pad : nullptr;
+    out->v_up = has_up ? P.base_up[slot] + L.pad : nullptr;
+    out->timeout = P.pull_timeout;
+    return true;
+}
+
+int dist_pull_timed_out(omg_hierarchy *h, bool *timed_out) {
+    *timed_out = false;
+    if (!h->peer.pull_timeout) return OMG_OK;
+    int f = 0;
+    CUDA_TRY(cudaMemcpy(&f, h->peer.pull_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out = f != 0;
+    return OMG_OK;
+}
+
+static int halo_exchange_now(omg_hierarchy *h, Level &L, double *v) {
     OMG_TRY(comm_fork());
     if (h->peer.enabled && peer_slot(L, 0, v) >= 0) {
         ProfScope ps(h, "halo_exchange", (int)(&L - h->lv.data()), 0.0, g.stream2);
@@ -395,6 +457,7 @@ int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v) {
 
 // the compute stream waits for every exchange started so far
 int dist_halo_wait(omg_hierarchy *h) {
+    if (!h->halo_req.empty()) OMG_TRY(dist_halo_flush(h));
     if (!h->halo_pending) return OMG_OK;
     CUDA_TRY(cudaStreamWaitEvent(g.stream, ev_join, 0));
     h->halo_pending = false;

@@ -130,6 +130,19 @@ struct PeerState {
     unsigned long long *flags_dn = nullptr, *flags_up = nullptr;   // the neighbours' flag arrays (mapped)
     std::vector<double *> base_dn, base_up;     // per slot: the neighbours' buffer base (mapped), slot = 2*level + (xb?1:0)
     std::vector<void *> opened;                 // everything cudaIpcOpenMemHandle returned
+    // fused halo pull (omg_stencil.cu k_st3 on slab levels): 8 words per slot
+    //   {kernels done, ready<-dn, ready<-up, arrivals, pulled<-dn, pulled<-up, -, -}
+    unsigned long long *pull = nullptr;                           // local
+    unsigned long long *pull_dn = nullptr, *pull_up = nullptr;    // the neighbours' arrays (mapped)
+    int *pull_timeout = nullptr;                // set by a kernel that gave up waiting for a neighbour
+    bool pull_ok = false;
+};
+
+// what a stencil kernel needs to read the halos of one vector of a slab level straight from the neighbours
+struct HaloPull {
+    unsigned long long *mine, *peer_dn, *peer_up;   // this slot's 8 words here and on the neighbours (nullptr: no neighbour)
+    const double *v_dn, *v_up;                      // the neighbours' copies of the vector (their owned row 0)
+    int *timeout;
 };
 
 struct omg_hierarchy {
@@ -152,6 +165,9 @@ struct omg_hierarchy {
     double *norm2_host = nullptr;    // pinned
     // state
     int cur0 = 0;                    // level-0 iterate lives in xa (0) or xb (1)
+    // halo exchanges asked for but not yet issued: the consuming stencil kernel may pull them itself (fused), any
+    // other consumer makes dist_halo_wait issue them on the comm stream
+    std::vector<std::pair<Level *, double *>> halo_req;
     std::map<CycleCfg, CachedGraph> graphs;
     std::map<CycleCfg, CachedGraph> gated;      // the same cycles behind the device-side stop test
     StopState *stop_dev = nullptr, *stop_host = nullptr;     // device / pinned
@@ -186,6 +202,9 @@ int run_cycle(omg_hierarchy *h, const CycleCfg &cfg);
 // omg_dist.cu
 int dist_halo_exchange(omg_hierarchy *h, Level &L, double *v);
 int dist_halo_wait(omg_hierarchy *h);
+int dist_halo_flush(omg_hierarchy *h);
+bool dist_pull_params(omg_hierarchy *h, Level &L, const double *v, HaloPull *out);
+int dist_pull_timed_out(omg_hierarchy *h, bool *timed_out);
 int dist_peer_setup(omg_hierarchy *h);
 void dist_peer_teardown(omg_hierarchy *h);
 int dist_allgather(omg_hierarchy *h, const double *piece, double *full, size_t count);

@@ -48,6 +48,16 @@ struct St3 {
     int cz0;               // global index of local coarse plane 0
     int colour;            // -1: all rows (Jacobi); 0/1: only rows of that grid-parity colour are relaxed
     int zlo, zhi, boundary;   // planes [zlo, zhi) in segments of ZL; `boundary`: CTA row 0 -> [0, zlo), row 1 -> [zhi, NZ)
+    // Fused halo pull (slab levels over NVLink peer memory, see st_pull_*): one grid of `nseg` interior segment rows
+    // plus two boundary rows ([0, zlo) and [zhi, NZ)) whose CTAs stage the planes -1 / NZ straight from the
+    // neighbours' copies of the vector once those are final.  pull == nullptr: not a fused launch.
+    unsigned long long *pull, *pull_dn, *pull_up;   // this slot's 8 flag words here / on the neighbours
+    const double *xi_dn, *xi_up;                    // the neighbours' copies of the staged vector (their owned row 0)
+    const double *e_dn, *e_up;                      // MODE 2: the neighbours' coarse correction (owned row 0)
+    int e_nzc;                                      // MODE 2: coarse planes of e this rank owns
+    int *pull_timeout;
+    int nseg;
+    int needs_fix;         // exception rows are corrected by fix-up kernels after this one (they read local halos)
     int use_cls;           // rows on the x/y grid boundaries get their class correction taps in-kernel (no fix-up)
     ClsTab cls;
     double d, c1, cS, cP, wod, w, omega;   // wod = omega/d
@@ -87,11 +97,78 @@ __device__ __forceinline__ void sts2(double *p, double2 v) { *reinterpret_cast<d
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 
+
+// ---------------------------------------------------------------- fused halo pull (compute + neighbour exchange in one kernel)
+//
+// Slab levels: the planes next to a cut need one plane (+ one row) of the neighbour's vector.  Instead of a separate
+// exchange (flag kernels + copy-engine pulls into local halo rows, then a second "boundary" launch behind a stream
+// dependency) the stencil kernel does it itself over NVLink peer memory.  Per (level, vector) slot, 8 words in
+// memory the neighbours have mapped: {kernels done, ready<-dn, ready<-up, arrivals, pulled<-dn, pulled<-up}.
+//   G = kernels done + 1 identifies this launch on every rank (all ranks run the same kernel sequence).
+//   CTA (0,0), first wave:   my vector is final (stream order) -> ready := G in both neighbours' words
+//   boundary CTAs, last rows: wait for ready<-neighbour >= G, then the TMA ring stages plane -1 / NZ from the
+//                            neighbour's copy (cp.async.bulk from the peer-mapped address); everything else is local
+//   last CTA to arrive:      pulled := G in both neighbours' words, wait until both have pulled from me (so nothing
+//                            that follows this kernel — not even a host copy — can overwrite rows still being
+//                            read), kernels done := G
+// The boundary planes of the OUTPUT are written by the boundary CTAs only, i.e. after the neighbours reported the
+// vector they are reading final, which orders them behind the neighbours' previous kernel: the ping-pong partner
+// of the staged vector is never overwritten while a neighbour still reads it.
+// Every wait is bounded (~4 s): on expiry a flag is raised (checked by the host after the solve) and the kernel
+// carries on, so a protocol error cannot hang the GPU.
+__device__ __forceinline__ void st_sys_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long st_sys_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_wait_ge(const unsigned long long *p, unsigned long long G, int *timeout_flag) {
+    const long long t0 = clock64();
+    while (st_sys_acquire(p) < G) {
+        if (clock64() - t0 > 8000000000ll) {
+            *timeout_flag = 1;
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+// thread 0 of CTA (0,0): publish; thread 0 of a boundary CTA: wait for the neighbour this piece reads from
+__device__ __forceinline__ void st_pull_begin(const St3 &P, int brow, unsigned long long G) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            __threadfence_system();
+            if (P.pull_dn) st_sys_release(P.pull_dn + 2, G);       // I am the up neighbour of dn
+            if (P.pull_up) st_sys_release(P.pull_up + 1, G);       // and the dn neighbour of up
+        }
+        if (brow == 0 && P.pull_dn) st_wait_ge(P.pull + 1, G, P.pull_timeout);
+        if (brow == 1 && P.pull_up) st_wait_ge(P.pull + 2, G, P.pull_timeout);
+        if (brow >= 0) asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (brow >= 0) __syncthreads();
+}
+// thread 0 of CTA (0,0) (after publishing) and of every boundary CTA (after its last plane)
+__device__ __forceinline__ void st_pull_arrive(const St3 &P, unsigned long long G, unsigned int nboundary) {
+    __threadfence_system();
+    if (atomicAdd(P.pull + 3, 1ull) == (unsigned long long)nboundary) {       // nboundary + 1 arrivals in all
+        P.pull[3] = 0ull;
+        if (P.pull_dn) st_sys_release(P.pull_dn + 5, G);       // "your up neighbour has pulled"
+        if (P.pull_up) st_sys_release(P.pull_up + 4, G);       // "your dn neighbour has pulled"
+        if (P.pull_dn) st_wait_ge(P.pull + 4, G, P.pull_timeout);
+        if (P.pull_up) st_wait_ge(P.pull + 5, G, P.pull_timeout);
+        __threadfence();
+        *(volatile unsigned long long *)P.pull = G;
+    }
+}
+
 // MODE 0: xo = xi + omega (b - A xi)/d
 // MODE 1: rc = R (b - A xi)
 // MODE 2: y = xi + R^T e ; xo = y + omega (b - A y)/d
 // MODE 3: xo = omega b/diag (first Jacobi sweep from x = 0) ; rc = R (b - A xo)      [xi == b]
-template <int MODE, int NT, bool CLS>
+// PULL: the fused-halo-pull instantiation (slab levels); the single-GPU instantiation carries none of its code — the
+// prolong+Jacobi kernel loses 15 % when merely compiled with it (0.57 -> 0.65 ms at 512^3).
+template <int MODE, int NT, bool CLS, bool PULL>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);
@@ -99,11 +176,43 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
     constexpr bool XF = (MODE == 2 || MODE == 3);
     const int NS = P.NS;
     const int tid = threadIdx.x;
-    const int z0 = P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL;
-    const int z1 = P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi);
+    // blockIdx.y: interior segment, or (fused-pull / boundary launches) one of the two boundary pieces
+    const int brow = PULL ? (int)blockIdx.y - P.nseg : -1;
+    const int z0 = PULL ? (brow >= 0 ? (brow == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL)
+                        : (P.boundary ? (blockIdx.y == 0 ? 0 : P.zhi) : P.zlo + (int)blockIdx.y * P.ZL);
+    const int z1 = PULL ? (brow >= 0 ? (brow == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi))
+                        : (P.boundary ? (blockIdx.y == 0 ? P.zlo : P.NZ) : min(z0 + P.ZL, P.zhi));
     const int y0 = blockIdx.x * P.TY;
     const long long span0 = (long long)y0 * P.S1 - P.S1;      // in-plane start of the span (row y0-1)
     const uint32_t span_bytes = (uint32_t)P.SPAN * 8u;
+    unsigned long long pullG = 0;
+    if constexpr (PULL) {
+        pullG = *(volatile unsigned long long *)P.pull + 1ull;     // stable until this launch's last arrival
+        st_pull_begin(P, brow, pullG);
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) st_pull_arrive(P, pullG, 2u * gridDim.x);
+    }
+    // Stage the span of plane p into ring slot k.  Fused pull: the part of the span below row 0 of the slab comes from
+    // the lower neighbour's copy of the vector, the part beyond the last row from the upper neighbour's (a span is
+    // whole rows, the slab a whole number of rows; the +-1-row halo of the first / last chunk makes the spans of the
+    // planes 0 and NZ-1 straddle a cut).  Without neighbour (or not fused): the local pad / halo rows.
+    auto issue_span = [&](int k, int p) {
+        const long long f0 = (long long)p * P.S2 + span0;
+        mbar_expect_tx(full + k, span_bytes);
+        double *dst = stage + (size_t)k * P.SPAN;
+        if constexpr (!PULL) {
+            bulk_g2s(dst, P.xi + f0, span_bytes, full + k);
+            return;
+        }
+        const long long f1 = f0 + P.SPAN, nl = (long long)P.NZ * P.S2;
+        long long a = f0, b = f1 < 0 ? f1 : 0;
+        if (b > a) bulk_g2s(dst, P.xi_dn ? P.xi_dn + (nl + a) : P.xi + a, (uint32_t)((b - a) * 8), full + k);
+        a = f0 > 0 ? f0 : 0;
+        b = f1 < nl ? f1 : nl;
+        if (b > a) bulk_g2s(dst + (a - f0), P.xi + a, (uint32_t)((b - a) * 8), full + k);
+        a = f0 > nl ? f0 : nl;
+        b = f1;
+        if (b > a) bulk_g2s(dst + (a - f0), P.xi_up ? P.xi_up + (a - nl) : P.xi + a, (uint32_t)((b - a) * 8), full + k);
+    };
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
@@ -115,8 +224,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
         for (int k = 0; k < NS; ++k) {
             int p = z0 - 1 + k;
             if (p > z1) break;
-            mbar_expect_tx(full + k, span_bytes);
-            bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+            if constexpr (PULL) {
+                issue_span(k, p);
+            } else {
+                mbar_expect_tx(full + k, span_bytes);
+                bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+            }
         }
     }
 
@@ -178,8 +291,19 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                     zz += 1;
                 }
                 double v = 0.0;
-                if (zz >= 0 && zz < P.NZg)
-                    v = __ldg(P.e + ((long long)((zz >> 1) - P.cz0) * P.cs1 + (yy >> 1)) * P.cs2 + (tx[k] >> 1));
+                if constexpr (!PULL) {
+                    if (zz >= 0 && zz < P.NZg)
+                        v = __ldg(P.e + ((long long)((zz >> 1) - P.cz0) * P.cs1 + (yy >> 1)) * P.cs2 + (tx[k] >> 1));
+                } else if (zz >= 0 && zz < P.NZg) {
+                    int cz = (zz >> 1) - P.cz0;
+                    const long long eo = (long long)(yy >> 1) * P.cs2 + (tx[k] >> 1);
+                    if (PULL && cz < 0 && P.e_dn)                   // the neighbours' coarse planes: NVLink loads
+                        v = __ldcv(P.e_dn + (long long)(cz + P.e_nzc) * P.cs1 * P.cs2 + eo);
+                    else if (PULL && cz >= P.e_nzc && P.e_up)
+                        v = __ldcv(P.e_up + (long long)(cz - P.e_nzc) * P.cs1 * P.cs2 + eo);
+                    else
+                        v = __ldg(P.e + (long long)cz * P.cs1 * P.cs2 + eo);
+                }
                 aux[k] = v;
             } else if (MODE == 3) {
                 unsigned m = 0u;
@@ -342,11 +466,16 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                 int k = (q - 1 + NS) % NS;      // == slot of plane z-1
                 // generic-proxy reads/writes of this slot are ordered before the async-proxy refill
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(full + k, span_bytes);
-                bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+                if constexpr (PULL) {
+                    issue_span(k, p);
+                } else {
+                    mbar_expect_tx(full + k, span_bytes);
+                    bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
+                }
             }
         }
     }
+    if (PULL && brow >= 0 && tid == 0) st_pull_arrive(P, pullG, 2u * gridDim.x);
 }
 
 // ---------------------------------------------------------------- split-row variant (rows wider than 2*NT)
@@ -1183,7 +1312,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
         int ns = (NZ + zl - 1) / zl;
         long long ctas = (long long)chunks * ns;
         long long waves = (ctas + slots - 1) / slots;
-        if (waves > 6) break;
+        if (waves > 12) break;      // (a cap of 6 left 256- and 512-chunk planes — the slab shapes — at 0.86 waves)
         double eff = (zl / (zl + 2.5)) * ((double)ctas / (double)(waves * slots));
         if (eff > best + 1e-9) {
             best = eff;
@@ -1203,6 +1332,7 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
         P->use_cls = 1;
         P->cls = L.cls;
     }
+    P->needs_fix = (L.kind == OMG_KIND_BAND_EXC && !P->use_cls) ? 1 : 0;
     return true;
 }
 
@@ -1213,7 +1343,8 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     static bool attr_set[2] = {false, false};
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
-    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256> : (P.use_cls ? k_st3<MODE, NT, true> : k_st3<MODE, NT, false>);
+    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256>
+                                    : (P.use_cls ? k_st3<MODE, NT, true, false> : k_st3<MODE, NT, false, false>);
     if (!attr_set[P.use_cls ? 1 : 0]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
@@ -1223,6 +1354,54 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     }
     const int chunks = (P.NYg / P.TY) * P.XC;
     const int ZB = 2;       // planes next to a slab cut: the only ones that read the halo planes
+    if (!SPLIT && !h->halo_req.empty() && !P.needs_fix && P.NZ >= 4 * ZB + 2) {
+        // fused pull: every pending exchange must be one this kernel can do itself (its staged vector, MODE 2: e)
+        HaloPull hx{}, he{};
+        bool ok = true, have_x = false, have_e = false;
+        int e_nzc = 0;
+        for (auto &r : h->halo_req) {
+            if (r.second == P.xi && !have_x) {
+                have_x = dist_pull_params(h, *r.first, r.second, &hx);
+                ok = ok && have_x;
+            } else if (MODE == 2 && r.second == P.e && !have_e) {
+                have_e = dist_pull_params(h, *r.first, r.second, &he);
+                ok = ok && have_e;
+                e_nzc = r.first->nloc / (P.cs1 * P.cs2);
+            } else {
+                ok = false;
+            }
+        }
+        if (ok && have_x) {
+            h->halo_req.clear();
+            P.pull = hx.mine;
+            P.pull_dn = hx.peer_dn;
+            P.pull_up = hx.peer_up;
+            P.xi_dn = hx.v_dn;
+            P.xi_up = hx.v_up;
+            P.pull_timeout = hx.timeout;
+            P.e_dn = have_e ? he.v_dn : nullptr;
+            P.e_up = have_e ? he.v_up : nullptr;
+            P.e_nzc = e_nzc;
+            P.boundary = 0;
+            P.zlo = ZB;
+            P.zhi = P.NZ - ZB;
+            P.nseg = (P.zhi - P.zlo + P.ZL - 1) / P.ZL;
+            if constexpr (!SPLIT) {
+                static bool attr_p[2] = {false, false};
+                void (*kp)(const St3) = P.use_cls ? k_st3<MODE, NT, true, true> : k_st3<MODE, NT, false, true>;
+                if (!attr_p[P.use_cls ? 1 : 0]) {
+                    if (cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                        cudaGetLastError();
+                        return false;
+                    }
+                    attr_p[P.use_cls ? 1 : 0] = true;
+                }
+                kp<<<dim3(chunks, P.nseg + 2), NT, smem, g.stream>>>(P);
+            }
+            return true;
+        }
+    }
+    if (!h->halo_req.empty()) dist_halo_flush(h);
     if (h->halo_pending && P.NZ >= 4 * ZB + 2) {
         // interior planes do not touch the halos: run them while the exchange is in flight
         P.boundary = 0;

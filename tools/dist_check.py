@@ -79,6 +79,12 @@ def main():
             err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-300)
             if rank == 0:
                 print("L%d %-18s max rel err %.2e%s" % (l, name, err, "  FAIL" if err > 1e-13 else ""), flush=True)
+                if err > 1e-13 and os.environ.get("OMG_DIST_DEBUG"):
+                    bad = np.nonzero(np.abs(got - want) > 1e-12 * np.abs(want).max())[0]
+                    shp = tuple(int(v) >> (l if out_level == l else l + 1) for v in shape)
+                    idx = np.array(np.unravel_index(bad, shp)).T
+                    print("    %d bad entries; leading-index values %s; first %s" % (
+                        len(bad), np.unique(idx[:, 0]).tolist()[:16], idx[:4].tolist()), flush=True)
             fails += err > 1e-13
 
     for smoother, pre, post in (("jacobi", 1, 1), ("jacobi", 2, 0), ("rbgs", 1, 1)):

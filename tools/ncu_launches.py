@@ -4,7 +4,8 @@ into one row per launch of the LAST V-cycle in the log: kernel, grid, block, tim
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -k regex:'^k_(st|fix|coarse_gemv|jacobi|residual|prolong|colour)' --csv --log-file gpurun_out/launches.csv \
         python tools/gpu_probe.py --cycles 2
-    python tools/ncu_launches.py gpurun_out/launches.csv 2 > profiles/<name>.csv [--traffic profiles/traffic.json]
+    python tools/ncu_launches.py gpurun_out/launches.csv 2 > profiles/<name>.csv \
+        [--traffic profiles/traffic.json --shape 512x512x512 --smoother jacobi|rbgs]
 
 Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py, not absolutes.
 """
@@ -48,11 +49,23 @@ def main():
     w.writerow(["", "cycle total", "", "", "%.2f" % total, "%.2f" % sum(p.get("rd", 0) for p in rows),
                 "%.2f" % sum(p.get("wr", 0) for p in rows), "1.0"])
     if traffic_out:
-        # the three level-0 kernels of a V(1,1) Jacobi cycle are the first two and the last launch
-        names = ["jacobi@L0", "residual_restrict@L0", "prolong_jacobi@L0"]
+        # the three level-0 kernels of a V(1,1) cycle are the first two and the last launch; bench.py looks the
+        # dominant kernel up under the workload shape ({"<shape>": {"<name>@L0": DRAM bytes per launch}, "source": ..})
+        shape = sys.argv[sys.argv.index("--shape") + 1] if "--shape" in sys.argv else "512x512x512"
+        smoother = sys.argv[sys.argv.index("--smoother") + 1] if "--smoother" in sys.argv else "jacobi"
+        names = {"jacobi": ["jacobi@L0", "residual_restrict@L0", "prolong_jacobi@L0"],
+                 "rbgs": ["rbgs_sweep@L0", "residual_restrict@L0", "prolong_rbgs_sweep@L0"]}[smoother]
         sel = [rows[0], rows[1], rows[-1]]
-        json.dump({k: (p.get("rd", 0) + p.get("wr", 0)) * 1e6 for k, p in zip(names, sel)}, open(traffic_out, "w"),
-                  indent=1)
+        try:
+            out = json.load(open(traffic_out))
+            if not isinstance(out.get(shape, {}), dict) or "source" not in out:
+                out = {}
+        except Exception:  # noqa: BLE001
+            out = {}
+        out.setdefault(shape, {}).update({k: (p.get("rd", 0) + p.get("wr", 0)) * 1e6 for k, p in zip(names, sel)})
+        out["source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch lists "
+                         "profiles/r2_launches_*.csv (python tools/gpu_probe.py --cycles 2), not measured in the timed run")
+        json.dump(out, open(traffic_out, "w"), indent=1)
 
 
 if __name__ == "__main__":
