@@ -12,19 +12,14 @@ run() {  # nproc shape... -- gl agg [--oracle]
   echo "rc=${PIPESTATUS[0]}" | tee -a $LOG
 }
 run 8 --shape 64 64 64 --gl 3 --agg 4096 --oracle
-run 8 --shape 512 16 512 --gl 4 --agg 16384 --oracle
 run 8 --shape 1024 16 1024 --gl 4 --agg 65536
 run 8 --shape 256 256 --gl 4 --agg 1024 --oracle
-run 8 --shape 262144 --gl 10 --agg 1024 --oracle
-run 4 --shape 64 64 64 --gl 3 --agg 4096 --oracle
 run 4 --shape 1024 16 1024 --gl 4 --agg 65536
 grep -c "FAIL" $LOG
-for n in 8 4 2; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29900 + n)) \
-      bench.py --gpus $n --steps 10 --warmup 3 --reps 3 > gpurun_out/r2_bench_n$n.json 2> gpurun_out/r2_bench_n$n.err
-  echo "bench n=$n rc=$?"; tail -c 400 gpurun_out/r2_bench_n$n.json
-done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29908 \
+    bench.py --gpus 8 --steps 10 --warmup 3 --reps 3 > gpurun_out/r2_bench_n8_pull.json 2> gpurun_out/r2_bench_n8_pull.err
+echo "bench n=8 pull rc=$?"; tail -c 300 gpurun_out/r2_bench_n8_pull.json
 OMG_AGGLOMERATE_BELOW=2097152 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29950 \
-    bench.py --gpus 8 --steps 10 --warmup 3 --reps 2 --no-extra > gpurun_out/r2_bench_n8_agg2m.json 2> gpurun_out/r2_bench_n8_agg2m.err
-echo "bench n=8 agg2m rc=$?"
+    bench.py --gpus 8 --steps 10 --warmup 3 --reps 2 --no-extra > gpurun_out/r2_bench_n8_pull_agg2m.json 2> gpurun_out/r2_bench_n8_pull_agg2m.err
+echo "bench n=8 pull agg2m rc=$?"
 nvidia-smi topo -m > gpurun_out/r2_topo.txt 2>&1
