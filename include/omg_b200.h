@@ -198,6 +198,11 @@ int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, d
                             int max_sweeps, int smoother, double omega, int *sweeps_done, double *norm);
 /* R_l (b - A_l x)  — getresidual + restriction (openmg/__init__.py:209-210), fused. rc has n_{l+1} entries. */
 int omg_residual_restrict(omg_hierarchy *h, int level, const double *b_host, const double *x_host, double *rc_host);
+/* The descent step of mgCycle on one level (openmg/__init__.py:201 pre-smoothing, :209-210 residual + restriction):
+ * x := smooth(A_l, b, x, sweeps) in/out, rc := R_l (b - A_l x) with n_{l+1} entries.  The last Jacobi sweep and the
+ * restricted residual run as one pass over x where the level allows it (k_jr3). */
+int omg_smooth_residual_restrict(omg_hierarchy *h, int level, const double *b_host, double *x_host, int sweeps,
+                                 int smoother, double omega, double *rc_host);
 /* x += R_l^T e   (openmg/__init__.py:214,224) */
 int omg_prolong_correct(omg_hierarchy *h, int level, const double *ec_host, double *x_host);
 /* smooth(A, b, x + R^T e, sweeps) (openmg/__init__.py:216-222), fused */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "omg_smooth_to_threshold": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, ctypes.c_double, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_double, c_i32p, c_f64p]),
     "omg_residual_restrict": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, c_f64p]),
+    "omg_smooth_residual_restrict": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_double, c_f64p]),
     "omg_prolong_correct": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p]),
     "omg_prolong_correct_smooth": (ctypes.c_int, [c_h, ctypes.c_int, c_f64p, c_f64p, c_f64p, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_double]),

@@ -37,6 +37,8 @@ int launch_resnorm2(omg_hierarchy *h, Level &L, double *x, const double *b, int 
 double *launch_smooth(omg_hierarchy *h, Level &L, int smoother, double omega, int sweeps, double *cur,
                       const double *b);
 int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b, double *rc);
+int launch_smooth_residual_restrict(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double **cur,
+                                    const double *b, double *rc);
 int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const double *xi, double *xo);
 double *launch_prolong_correct_smooth(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double *cur,
                                       double *e, const double *b, bool cur_halo_valid);
@@ -900,6 +902,22 @@ int omg_residual_restrict(omg_hierarchy *h, int level, const double *b_host, con
     OMG_TRY(up(L, L.b, b_host));
     OMG_TRY(up(L, L.xa, x_host));
     OMG_TRY(launch_residual_restrict(h, level, L.xa, L.b, C.b));
+    return down(C, rc_host, C.b);
+}
+
+int omg_smooth_residual_restrict(omg_hierarchy *h, int level, const double *b_host, double *x_host, int sweeps,
+                                 int smoother, double omega, double *rc_host) {
+    CHECK_LEVEL(h, level);
+    if (level >= h->nlev - 1) return omg_set_error(OMG_EINVAL, "level %d has no restriction", level);
+    OMG_TRY(check_cfg(h, sweeps, 0, smoother, omega));
+    Level &L = h->lv[level];
+    Level &C = h->lv[level + 1];
+    OMG_TRY(up(L, L.b, b_host));
+    OMG_TRY(up(L, L.xa, x_host));
+    double *cur = L.xa;
+    OMG_TRY(launch_smooth_residual_restrict(h, level, smoother, omega, sweeps, &cur, L.b, C.b));
+    if (level == 0) h->cur0 = (cur == L.xb);
+    OMG_TRY(down(L, x_host, cur));
     return down(C, rc_host, C.b);
 }
 

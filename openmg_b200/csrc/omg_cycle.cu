@@ -177,6 +177,35 @@ int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b
     return OMG_OK;
 }
 
+// pre-smoothing + restricted residual (openmg/__init__.py:201, :209-210): `sweeps` sweeps from *cur (nullptr = zero
+// iterate), then b_{l+1} = R_l (b_l - A_l x).  A last Jacobi sweep from a non-zero iterate and the restricted residual
+// run as ONE pass over x where the level allows it (k_jr3).  *cur: the buffer holding the smoothed iterate.
+int launch_smooth_residual_restrict(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double **cur,
+                                    const double *b, double *rc) {
+    Level &L = h->lv[l];
+    Level &C = h->lv[l + 1];
+    if (smoother == OMG_SMOOTH_JACOBI && sweeps >= 1 && (*cur != nullptr || sweeps >= 2) && L.regular &&
+        !(h->flags & OMG_FLAG_NO_FUSED) &&
+        stencil_jacobi_residual_restrict(h, L, C, nullptr, nullptr, nullptr, nullptr, omega)) {     // applicability probe
+        double *c = launch_smooth(h, L, smoother, omega, sweeps - 1, *cur, b);
+        double *out = other(L, c);
+        bool ok;
+        {
+            ProfScope ps(h, "jacobi_residual_restrict", l, 24.0 * L.nloc + 8.0 * L.piece_n);
+            ok = stencil_jacobi_residual_restrict(h, L, C, c, b, out, V(C, rc), omega);
+        }
+        if (ok) {
+            h->launches++;
+            *cur = out;
+            return OMG_OK;
+        }
+        *cur = launch_smooth(h, L, smoother, omega, 1, c, b);      // launch failed after a successful probe
+        return launch_residual_restrict(h, l, *cur, b, rc);
+    }
+    *cur = launch_smooth(h, L, smoother, omega, sweeps, *cur, b);
+    return launch_residual_restrict(h, l, *cur, b, rc);
+}
+
 // xo = xi + R_l^T e   (xo may alias xi)
 int launch_prolong_correct(omg_hierarchy *h, int l, const double *e, const double *xi, double *xo) {
     Level &L = h->lv[l];
@@ -302,10 +331,7 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
             dist_halo_wait(h);      // the real launch failed after a successful probe: generic path from the zero iterate
         }
     }
-    if (!fused0) {
-        cur = launch_smooth(h, L, cfg.smoother, cfg.omega, cfg.pre, cur, L.b);
-        launch_residual_restrict(h, l, cur, L.b, C.b);
-    }
+    if (!fused0) launch_smooth_residual_restrict(h, l, cfg.smoother, cfg.omega, cfg.pre, &cur, L.b, C.b);
     double *e = cycle_level(h, l + 1, cfg, nullptr);
     // cur's halos were filled for the restriction (unfused path) and cur has not changed since
     return launch_prolong_correct_smooth(h, l, cfg.smoother, cfg.omega, cfg.post, cur, e, L.b, !fused0);

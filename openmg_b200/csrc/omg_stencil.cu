@@ -2366,3 +2366,301 @@ bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double
     Q.colour = 0;
     return st2rb_launch<2>(h, Q);
 }
+
+// ================================================================ 3-D Jacobi sweep + residual + restriction in one pass
+//
+// The last pre-smoothing sweep of a level and the restricted residual that follows it (openmg/__init__.py:201 and
+// :209-210) in ONE pass over x: x and b are read once, the new iterate and the coarse right-hand side written once —
+// 24 n + 8 n_c bytes instead of 24 n for the sweep plus 16 n + 8 n_c for the residual.  Temporal blocking in z on
+// the skeleton of k_rb3 (full-row chunks of TY rows, one TMA bulk copy per raw plane with two halo rows per side,
+// 3-stage mbarrier ring, one __syncthreads per plane):
+//   pass A(p)   Jacobi on EVERY point of plane p from the RAW planes p-1, p, p+1  -> "mid" plane p in shared memory,
+//               and, for the planes the segment owns, the new iterate in global memory
+//   pass B(p-1) residual of plane p-1 from the MID planes p-2, p-1, p, summed over the 2x2 patch and over the plane
+//               pair of the aggregate                                             -> one coarse value per patch
+// Pass B needs mid one row beyond the chunk and one plane beyond the segment: pass A also runs on the rows y0-1 and
+// y0+TY (one x-pair per thread) and on the planes z0-1 and z1, recomputed with the same expression as the owner's and
+// never stored.
+// The restriction only wants the SUM of the residual over an aggregate, and a 2x2 patch on even rows/columns is one
+// plane of an aggregate, so pass B never forms a point residual:
+//   sum_patch (A x)(p-1) = (d + c1 + cS) S(p-1) + c1 (left + right columns) + cS (row above + row below)
+//                          + cP (S(p-2) + S(p)),          S(q) = sum of the thread's own patch of mid plane q
+// — two scalars carried in registers per patch, 2 LDS.128 + 4 LDS.64 from mid plane p-1, a dozen flops.  The result
+// differs from the point-wise evaluation by rounding only (different summation order).
+// Flat-index semantics (openmg/operators.py:244-256) as in k_rb3: full rows make the x-wraps contiguous, halo rows of
+// the first / last chunk are rows of the neighbouring plane and are relaxed iff the point they really are lies in
+// [0,n); everything outside [0,n) is the zero pad and stays zero in mid.
+// Pure band levels only (level 0 of the Poisson hierarchies — the only level whose pre-smoothing does not start from
+// the zero iterate when nu1 = 1), unsharded.
+#define JR3_NT 512
+#define JR3_PPT 2
+
+struct Jr3 {
+    const double *xi;
+    const double *b;
+    double *xo;
+    double *rc;
+    int S1, S2, NY, NZ;    // row length, plane size, rows per plane, planes
+    int TY, ZL;            // rows per chunk, planes per z-segment (even)
+    int RS, MS;            // staged raw plane (TY+4 rows) / mid plane (TY+2 rows) in doubles
+    int cs1, cs2;          // coarse rows per plane, coarse row length
+    double d, c1, cS, cP, wod, w, dsum;     // wod = omega/d, dsum = d + c1 + cS
+};
+
+__device__ __forceinline__ double jr3_relax(const Jr3 &P, double c, double l, double r, double n, double s, double zm,
+                                            double zp, double b) {
+    const double ax = P.d * c + P.c1 * (l + r) + P.cS * (n + s) + P.cP * (zm + zp);
+    return c + P.wod * (b - ax);
+}
+
+__global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NT = JR3_NT, NS = 3, NM = 2;
+    constexpr int KS = 4 * NT;             // slot k+1 is NT patches = 2 NT / HX patch rows = 4 NT doubles further on
+    const int S1 = P.S1, HX = S1 >> 1;
+    const int RS = P.RS, MS = P.MS;
+    double *raw = reinterpret_cast<double *>(smem_raw);
+    double *mid = raw + (size_t)NS * RS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(mid + NM * (size_t)MS);
+    const int tid = threadIdx.x;
+    const int y0 = (int)blockIdx.x * P.TY;
+    const int z0 = (int)blockIdx.y * P.ZL;
+    const int z1 = min(z0 + P.ZL, P.NZ);
+    const uint32_t span_bytes = (uint32_t)RS * 8u;
+    const int pfirst = max(z0 - 2, -1);           // raw planes below -1 / above NZ are all zero and never staged
+    const int plast = min(z1 + 1, P.NZ);
+    const long long gbase = (long long)(y0 - 2) * S1;      // staged offset o <-> in-plane offset gbase + o
+
+    auto slot_of = [&](int p) { return (p - pfirst) % NS; };
+    auto issue = [&](int p) {
+        int s_ = slot_of(p);
+        mbar_expect_tx(full + s_, span_bytes);
+        bulk_g2s(raw + (size_t)s_ * RS, P.xi + (long long)p * P.S2 + gbase, span_bytes, full + s_);
+    };
+    auto wait_plane = [&](int p) {
+        int k = p - pfirst;
+        mbar_wait(full + (k % NS), (uint32_t)((k / NS) & 1));
+    };
+
+    if (tid == 0) {
+        for (int s_ = 0; s_ < NS; ++s_) mbar_init(full + s_, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int p = pfirst; p < pfirst + NS && p <= plast; ++p) issue(p);
+
+    // work items as in k_rb3: slot k of thread tid is the 2x2 patch tid + k NT of the chunk (passes A and B); the halo
+    // item is one x-pair of the grid row y0-1 (threads [0,HX)) or y0+TY (threads [HX,2HX)), pass A only.
+    const int nslots = ((P.TY >> 1) * HX) / NT;          // 1 or 2 (host: TY/2 * HX is a multiple of NT)
+    const int pj = tid / HX, pi_ = tid - pj * HX;
+    const int ro = (2 * pj + 2) * S1 + 2 * pi_;          // row a of slot 0 inside a staged raw plane; mid: ro - S1
+    const bool hact = tid < 2 * HX;
+    const bool hwhich = tid >= HX;
+    const int ho = (hwhich ? (P.TY + 2) * S1 + 2 * (tid - HX) : S1 + 2 * tid);
+    const bool hwrap = hwhich ? (y0 + P.TY == P.NY) : (y0 == 0);
+    const int hshift = hwrap ? (hwhich ? 1 : -1) : 0;     // the plane the halo row really belongs to: p + hshift
+
+    // carried from plane to plane, per slot: the raw patch of plane p-1 (z- neighbours of pass A), the patch sums of
+    // the mid planes p-1 and p-2 and of b on plane p-1 (pass B), the b patch of plane p (fetched one step ahead),
+    // the residual sum of the open aggregate.
+    double2 za[JR3_PPT], zb[JR3_PPT], ba[JR3_PPT], bb[JR3_PPT];
+    double s1[JR3_PPT], s2[JR3_PPT], sb[JR3_PPT], acc[JR3_PPT];
+    double2 hz = make_double2(0.0, 0.0), hb = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < JR3_PPT; ++k) {
+        za[k] = zb[k] = ba[k] = bb[k] = make_double2(0.0, 0.0);
+        s1[k] = s2[k] = sb[k] = acc[k] = 0.0;
+    }
+
+    if (z0 - 2 >= pfirst) wait_plane(z0 - 2);
+    // step z0-2 only fills the register pipeline (raw patch of plane z0-2, b of plane z0-1)
+    for (int p = z0 - 2; p <= z1; ++p) {
+        const bool real = p >= z0 - 1;
+        const bool relax = real && p >= 0 && p < P.NZ;
+        const bool has_cur = (p >= pfirst && p <= plast);
+        const bool has_next = (p + 1 >= pfirst && p + 1 <= plast);
+        if (has_next) wait_plane(p + 1);
+        const double *rawc = raw + (size_t)slot_of(max(p, pfirst)) * RS;
+        const double *rawn = raw + (size_t)slot_of(max(p + 1, pfirst)) * RS;
+        const int mq = p - z0 + 2 + NM;                                     // mid plane p lives in slot mq % NM
+        double *midw = mid + (size_t)(mq % NM) * MS - S1;                  // mid row = staged row - 1
+        const double *midp = mid + (size_t)((mq - 1) % NM) * MS - S1;
+        const bool owned = p >= z0 && p < z1;
+        const bool doB = p - 1 >= z0;
+        const bool bnext = (p + 1 >= max(z0 - 1, 0)) && (p + 1 <= min(z1, P.NZ - 1));
+        double *outp = P.xo + (long long)p * P.S2 + gbase;
+        const double *bpn = P.b + (long long)(p + 1) * P.S2 + gbase;
+#pragma unroll
+        for (int k = 0; k < JR3_PPT; ++k) {
+            if (k >= nslots) continue;
+            const int o = ro + k * KS;
+            double2 ra = make_double2(0.0, 0.0), rb = ra;
+            if (has_cur) {
+                ra = lds2(rawc + o);
+                rb = lds2(rawc + o + S1);
+            }
+            double2 na = ra, nb = rb;
+            if (relax) {
+                // ---- pass A
+                double2 pa = make_double2(0.0, 0.0), pb = pa;
+                if (has_next) {
+                    pa = lds2(rawn + o);
+                    pb = lds2(rawn + o + S1);
+                }
+                const double2 vn = lds2(rawc + o - S1), vs = lds2(rawc + o + 2 * S1);
+                const double la = rawc[o - 1], rra = rawc[o + 2], lb = rawc[o + S1 - 1], rrb = rawc[o + S1 + 2];
+                na.x = jr3_relax(P, ra.x, la, ra.y, vn.x, rb.x, za[k].x, pa.x, ba[k].x);
+                na.y = jr3_relax(P, ra.y, ra.x, rra, vn.y, rb.y, za[k].y, pa.y, ba[k].y);
+                nb.x = jr3_relax(P, rb.x, lb, rb.y, ra.x, vs.x, zb[k].x, pb.x, bb[k].x);
+                nb.y = jr3_relax(P, rb.y, rb.x, rrb, ra.y, vs.y, zb[k].y, pb.y, bb[k].y);
+                if (owned) {
+                    *reinterpret_cast<double2 *>(outp + o) = na;
+                    *reinterpret_cast<double2 *>(outp + o + S1) = nb;
+                }
+            }
+            if (real) {
+                // mid plane p (planes -1 and NZ: nothing was relaxed, it is the all-zero raw plane)
+                sts2(midw + o, na);
+                sts2(midw + o + S1, nb);
+            }
+            const double s0 = (na.x + na.y) + (nb.x + nb.y);
+            if (doB) {
+                // ---- pass B: patch sum of the residual of plane p-1
+                const double2 mn = lds2(midp + o - S1), ms = lds2(midp + o + 2 * S1);
+                const double ml = midp[o - 1] + midp[o + S1 - 1], mr = midp[o + 2] + midp[o + S1 + 2];
+                const double ax = P.dsum * s1[k] + P.c1 * (ml + mr) + P.cS * ((mn.x + mn.y) + (ms.x + ms.y)) +
+                                  P.cP * (s2[k] + s0);
+                double a = acc[k] + (sb[k] - ax);
+                if ((p - 1) & 1) {
+                    P.rc[((long long)((p - 1) >> 1) * P.cs1 + (y0 >> 1) + pj + k * (NT / HX)) * P.cs2 + pi_] = P.w * a;
+                    a = 0.0;
+                }
+                acc[k] = a;
+            }
+            s2[k] = s1[k];
+            s1[k] = s0;
+            sb[k] = (ba[k].x + ba[k].y) + (bb[k].x + bb[k].y);
+            za[k] = ra;
+            zb[k] = rb;
+            if (bnext) {
+                ba[k] = ldg2(bpn + o);
+                bb[k] = ldg2(bpn + o + S1);
+            }
+        }
+        if (hact) {
+            // the halo item's row may belong to the neighbouring plane: relaxed iff that point lies inside [0,n)
+            double2 hr = make_double2(0.0, 0.0);
+            if (has_cur) hr = lds2(rawc + ho);
+            double2 hm = hr;
+            if (real && p + hshift >= 0 && p + hshift < P.NZ) {
+                double2 hp = make_double2(0.0, 0.0);
+                if (has_next) hp = lds2(rawn + ho);
+                const double2 hn = lds2(rawc + ho - S1), hs = lds2(rawc + ho + S1);
+                const double hl = rawc[ho - 1], hrr = rawc[ho + 2];
+                hm.x = jr3_relax(P, hr.x, hl, hr.y, hn.x, hs.x, hz.x, hp.x, hb.x);
+                hm.y = jr3_relax(P, hr.y, hr.x, hrr, hn.y, hs.y, hz.y, hp.y, hb.y);
+            }
+            if (real) sts2(midw + ho, hm);
+            hz = hr;
+            if (p + 1 >= z0 - 1 && p + 1 <= z1 && p + 1 + hshift >= 0 && p + 1 + hshift < P.NZ)
+                hb = ldg2(P.b + (long long)(p + 1) * P.S2 + gbase + ho);
+        }
+        __syncthreads();        // raw plane p and mid plane p-1 are free, mid plane p is complete
+        if (tid == 0 && p >= pfirst && p + NS <= plast) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(p + NS);       // into the slot of plane p
+        }
+    }
+}
+
+static bool jr3_params(Level &L, Jr3 *P) {
+    if (getenv("OMG_NO_JR3") != nullptr) return false;      // read per call: the parity test runs both paths
+    if (L.kind != OMG_KIND_BAND || L.slab || L.band.nb != 6) return false;
+    const BandOp &B = L.band;
+    if (B.off[3] != 1 || B.off[2] != -1 || B.off[4] != -B.off[1] || B.off[5] != -B.off[0]) return false;
+    if (B.coef[2] != B.coef[3] || B.coef[1] != B.coef[4] || B.coef[0] != B.coef[5]) return false;
+    int S1 = B.off[4], S2 = B.off[5];
+    if (S1 < 64 || (S1 & 63) || S2 % S1 != 0 || L.n % S2 != 0) return false;     // patch rows must be warp-uniform
+    int NY = S2 / S1, NZ = L.n / S2;
+    if ((NY & 1) || NY < 4 || (NZ & 1) || NZ < 2) return false;
+    if (L.pad < S2 + 2 * S1) return false;        // plane -1 is staged from row y0-2
+    if (!(L.regular && L.reg.alpha == 3 && L.reg.fs2 == S1 && L.reg.fs1 == NY)) return false;
+    const int NT = JR3_NT;
+    int TY = 0;
+    for (int t = std::min(env_int("OMG_JR3_TY", 64), NY); t >= 2; --t) {
+        if ((t & 1) || NY % t != 0) continue;
+        if ((t / 2) * (S1 / 2) > NT * JR3_PPT || ((t / 2) * (S1 / 2)) % NT != 0 || S1 > NT) continue;   // whole slots; one halo item per thread
+        size_t smem = ((size_t)3 * (t + 4) + (size_t)2 * (t + 2)) * S1 * 8 + 64;
+        if (smem > 227 * 1024) continue;
+        TY = t;
+        break;
+    }
+    if (TY < 2) return false;
+    P->S1 = S1;
+    P->S2 = S2;
+    P->NY = NY;
+    P->NZ = NZ;
+    P->TY = TY;
+    P->RS = (TY + 4) * S1;
+    P->MS = (TY + 2) * S1;
+    P->cs1 = NY / 2;
+    P->cs2 = S1 / 2;
+    P->d = B.diag;
+    P->c1 = B.coef[3];
+    P->cS = B.coef[4];
+    P->cP = B.coef[5];
+    P->dsum = B.diag + B.coef[3] + B.coef[4];
+    {   // z-segments of even length: 3 extra steps + ~1.5 planes of pipeline ramp per segment against whole waves of
+        // one CTA per SM
+        int chunks = NY / TY, slots = std::max(g.sm_count, 1);
+        int ZL = NZ;
+        double best = -1.0;
+        for (int nseg = 1; nseg <= NZ / 2; ++nseg) {
+            int zl = (NZ + nseg - 1) / nseg;
+            zl += zl & 1;
+            int ns = (NZ + zl - 1) / zl;
+            long long ctas = (long long)chunks * ns;
+            long long waves = (ctas + slots - 1) / slots;
+            if (waves > 16) break;
+            double eff = (zl / (zl + 4.5)) * ((double)ctas / (double)(waves * slots));
+            if (eff > best + 1e-9) {
+                best = eff;
+                ZL = zl;
+            }
+        }
+        int envZL = env_int("OMG_JR3_ZL", 0);
+        if (envZL >= 2) ZL = envZL + (envZL & 1);
+        P->ZL = std::min(std::max(ZL, 2), NZ);
+    }
+    return true;
+}
+
+// xo = xi + omega (b - A xi)/diag ; rc = R (b - A xo) — the last pre-smoothing sweep and the restricted residual in a
+// single pass.  xi == nullptr: applicability probe.
+bool stencil_jacobi_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *b,
+                                      double *xo, double *rcv, double omega) {
+    (void)C;
+    Jr3 P{};
+    if (!jr3_params(L, &P)) return false;
+    if (!xi) return true;
+    P.xi = xi;
+    P.b = b;
+    P.xo = xo;
+    P.rc = rcv + L.piece_row0;
+    P.w = L.Rw;
+    P.wod = omega / P.d;
+    static bool attr_set = false;
+    size_t smem = ((size_t)3 * P.RS + (size_t)2 * P.MS) * sizeof(double) + 64;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_jr3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_set = true;
+    }
+    dist_halo_wait(h);
+    k_jr3<<<dim3(P.NY / P.TY, (P.NZ + P.ZL - 1) / P.ZL), JR3_NT, smem, g.stream>>>(P);
+    return true;
+}

@@ -176,6 +176,15 @@ class _Handle(object):
         check(self._L.omg_residual_restrict(self._h, level, f64(bb), f64(xx), f64(rc)))
         return rc
 
+    def smooth_residual_restrict(self, level, b, x, sweeps, smoother="jacobi", omega=0.8):
+        """The descent step of a cycle on one level (openmg/__init__.py:201,209-210): returns (smoothed x, R (b - A x))."""
+        n = self.n(level)
+        bb, xx = _vec(b, n, "b"), _vec(x, n, "x").copy()
+        rc = np.empty(self.n(level + 1), np.float64)
+        check(self._L.omg_smooth_residual_restrict(self._h, level, f64(bb), f64(xx), int(sweeps), SMOOTHERS[smoother],
+                                                   float(omega), f64(rc)))
+        return xx, rc
+
     def prolong_correct(self, level, ec, x):
         xx = _vec(x, self.n(level), "x").copy()
         ee = _vec(ec, self.n(level + 1), "e")

@@ -152,6 +152,10 @@ def test_bench_kernel_instantiations_vs_oracle(shape, gl):
         assert rel(h.residual_restrict(l, b, x), R[l].dot(b - Al.dot(x))) <= 1e-13
         assert rel(h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8), orc.jacobi(Al, b, y.copy(), 1, 0.8)) <= 1e-12
         assert rel(h.prolong_correct_smooth(l, b, e, x, 2, "rbgs"), orc.rbgs(Al, b, y.copy(), 2, col)) <= 1e-10
+        # descent step: sweep + restricted residual (level 0 of the 512-wide shapes: the single-pass kernel k_jr3)
+        xs, rc = h.smooth_residual_restrict(l, b, x, 1, "jacobi", 0.8)
+        xw = orc.jacobi(Al, b, x.copy(), 1, 0.8)
+        assert rel(xs, xw) <= 1e-12 and rel(rc, R[l].dot(b - Al.dot(xw))) <= 1e-13
     # whole cycles (the zero-start sweep + residual + restriction kernel only runs inside a cycle)
     u = np.random.RandomState(0).random_sample(A0.shape[0])
     b = A0.dot(u)

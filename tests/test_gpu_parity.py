@@ -241,6 +241,45 @@ def test_3d_single_pass_two_colour_sweep(shape, gl, monkeypatch):
             close(outs[True][ci][i], outs[False][ci][i], 1e-13, "single-pass vs half-sweeps, L%d case %d" % (l, i))
 
 
+@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 2), ((64, 32, 64), 2), ((128, 128, 128), 3), ((256, 16, 256), 3),
+                                      ((256, 32, 256), 3), ((512, 16, 512), 3)])
+def test_3d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, monkeypatch):
+    """k_jr3 (the last pre-smoothing Jacobi sweep and the restricted residual of openmg/__init__.py:201,209-210 in
+    one pass over x) against the oracle and against the two separate kernels (OMG_NO_JR3): first/last chunks and
+    segments (flat-index wraps into the neighbouring planes), one and two patch slots per thread, 64- to 512-wide
+    rows, with and without preceding sweeps."""
+    A0 = sp.csr_matrix(orc.poisson_csr(shape))
+    R = orc.restrictionList(shape, gl - 1, 8)
+    n = A0.shape[0]
+    rs = np.random.RandomState(29)
+    x, b = rs.random_sample(n), rs.random_sample(n)
+    outs = {}
+    for on in (False, True):
+        if on:
+            monkeypatch.delenv("OMG_NO_JR3", raising=False)
+        else:
+            monkeypatch.setenv("OMG_NO_JR3", "1")
+        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+        outs[on] = [h.smooth_residual_restrict(0, b, x, sweeps, "jacobi", 0.8) for sweeps in (1, 2, 3)]
+        outs[on].append(h.smooth_residual_restrict(0, b, np.zeros(n), 1, "jacobi", 0.8))
+        h.close()
+    wants = [orc.jacobi(A0, b, x.copy(), sweeps, 0.8) for sweeps in (1, 2, 3)] + [orc.jacobi(A0, b, np.zeros(n), 1, 0.8)]
+    for i, xw in enumerate(wants):
+        rw = R[0].dot(b - A0.dot(xw))
+        close(outs[True][i][0], xw, JAC_RTOL, "x, case %d" % i)
+        close(outs[True][i][1], rw, 1e-13, "R r, case %d" % i)
+        close(outs[True][i][0], outs[False][i][0], 1e-15, "x: single pass vs two kernels, case %d" % i)
+        close(outs[True][i][1], outs[False][i][1], 1e-13, "R r: single pass vs two kernels, case %d" % i)
+    # small residuals: the patch-sum form of the residual must not lose accuracy when b - A x cancels
+    xs = rs.random_sample(n)
+    bs = A0.dot(xs)
+    h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+    xg, rg = h.smooth_residual_restrict(0, bs, xs, 1, "jacobi", 0.8)
+    h.close()
+    close(xg, xs, 1e-14, "x already solves A x = b: the sweep leaves it alone")
+    assert np.abs(rg).max() <= 1e-12 * np.abs(bs).max(), "x already solves A x = b: restricted residual at rounding level"
+
+
 def test_band_detection_reports_structure():
     h = Hierarchy(orc.poisson_csr((32, 32, 32)), (32, 32, 32), 2, 8)
     i0, i1 = h.level_info(0), h.level_info(1)
