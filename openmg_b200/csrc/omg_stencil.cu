@@ -57,6 +57,8 @@ struct St3 {
     int e_nzc;                                      // MODE 2: coarse planes of e this rank owns
     int *pull_timeout;
     int nseg;
+    int bpf;               // planes by which thread 0 prefetches b into L2 ahead of its loads (0: off)
+    int epf;               // the same for the coarse correction e (MODE 2), in fine planes
     int needs_fix;         // exception rows are corrected by fix-up kernels after this one (they read local halos)
     int use_cls;           // rows on the x/y grid boundaries get their class correction taps in-kernel (no fix-up)
     ClsTab cls;
@@ -90,6 +92,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+// TMA bulk prefetch into L2 (no destination, no registers): thread 0 pulls the b rows a later step will load with
+// ld.global.nc out of HBM ahead of time, so those loads are L2 hits instead of exposed DRAM latency.
+__device__ __forceinline__ void bulk_prefetch_l2(const double *src, long long lo, long long hi) {
+    if (hi > lo)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + lo), "r"((uint32_t)((hi - lo) * 8))
+                     : "memory");
 }
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -472,6 +482,16 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                     mbar_expect_tx(full + k, span_bytes);
                     bulk_g2s(stage + (size_t)k * P.SPAN, P.xi + (long long)p * P.S2 + span0, span_bytes, full + k);
                 }
+            }
+            if (!PULL && P.bpf > 0 && z + P.bpf < z1) {
+                const long long bo = (long long)(z + P.bpf) * P.S2 + (long long)y0 * P.S1;
+                bulk_prefetch_l2(P.b, bo, bo + (long long)P.TY * P.S1);
+            }
+            if (!PULL && MODE == 2 && P.epf > 0 && z + P.epf <= z1 && ((z + P.epf) & 1) == 0) {
+                // coarse correction of the plane pair starting at z + epf: coarse rows y0/2 - 1 .. (y0 + TY)/2
+                const long long nc = (long long)(P.NZg >> 1) * P.cs1 * P.cs2;
+                const long long eo = ((long long)(((z + P.epf + P.zg0) >> 1) - P.cz0) * P.cs1 + (y0 >> 1) - 1) * P.cs2;
+                bulk_prefetch_l2(P.e, max(eo, 0ll), min(eo + (long long)((P.TY >> 1) + 2) * P.cs2, nc));
             }
         }
     }
@@ -1327,6 +1347,8 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->ZL = ZL;
     P->has_exc = 0;
     P->colour = -1;
+    P->bpf = env_int("OMG_BPF", 2);
+    P->epf = env_int("OMG_EPF", 4);
     P->use_cls = 0;
     if (L.kind == OMG_KIND_BAND_EXC && L.classed && XH == 0) {
         P->use_cls = 1;
@@ -1855,6 +1877,8 @@ struct Rb3 {
     int RS, MS;            // staged raw plane (TY+4 rows) / mid plane (TY+2 rows) in doubles
     int cs1, cs2;          // coarse rows per plane, coarse row length
     int c0;                // colour relaxed first
+    int bpf;               // planes by which thread 0 prefetches b into L2 ahead of its loads (0: off)
+    int epf;               // the same for the coarse correction e (MODE 2), in fine planes
     ClsTab cls;            // Galerkin levels (CLS): class correction taps on the x/y grid boundaries
     double d, c1, cS, cP, wod, w;
 };
@@ -2199,6 +2223,23 @@ __global__ void __launch_bounds__(RB3_NT, 1) k_rb3(const Rb3 P) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(p - KEEP + NS);       // into the slot of plane p-KEEP
         }
+        if (!CLS && MODE != 3 && tid == 0 && P.bpf > 0) {      // (level 0; the CLS variants have no register to spare)
+            // b of plane q (rows y0-1 .. y0+TY) is loaded at the end of step q-1
+            const int q = p + 1 + P.bpf;
+            if (q >= 0 && q <= min(z1, P.NZ - 1)) {
+                const long long lo = (long long)q * P.S2 + gbase + S1, nn = (long long)P.NZ * P.S2;
+                bulk_prefetch_l2(P.b, max(lo, 0ll), min(lo + (long long)(P.TY + 2) * S1, nn));
+            }
+        }
+        if (!CLS && MODE == 2 && tid == 0 && P.epf > 0) {
+            // e of raw plane q is fetched two steps before the plane is used: coarse rows y0/2 - 1 .. (y0 + TY)/2
+            const int q = p + P.epf;
+            if ((q & 1) == 0 && q >= 0 && q < P.NZ) {
+                const long long nc = (long long)(P.NZ >> 1) * P.cs1 * P.cs2;
+                const long long eo = ((long long)(q >> 1) * P.cs1 + (y0 >> 1) - 1) * P.cs2;
+                bulk_prefetch_l2(P.e, max(eo, 0ll), min(eo + (long long)((P.TY >> 1) + 2) * P.cs2, nc));
+            }
+        }
     };
 
     // start on a DG = 0 plane at or below z0-2: at least one fill step precedes the first relaxed plane z0-1
@@ -2257,6 +2298,8 @@ static bool rb3_params(Level &L, Rb3 *P, bool *use_cls, bool need_regular) {
     P->cs1 = NY / 2;
     P->cs2 = S1 / 2;
     P->c0 = 0;
+    P->bpf = env_int("OMG_BPF", 2);
+    P->epf = env_int("OMG_EPF", 4);
     P->d = B.diag;
     P->c1 = B.coef[3];
     P->cS = B.coef[4];
@@ -2404,6 +2447,7 @@ struct Jr3 {
     int TY, ZL;            // rows per chunk, planes per z-segment (even)
     int RS, MS;            // staged raw plane (TY+4 rows) / mid plane (TY+2 rows) in doubles
     int cs1, cs2;          // coarse rows per plane, coarse row length
+    int bpf;               // planes by which thread 0 prefetches b into L2 ahead of its loads (0: off)
     double d, c1, cS, cP, wod, w, dsum;     // wod = omega/d, dsum = d + c1 + cS
 };
 
@@ -2572,6 +2616,14 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(p + NS);       // into the slot of plane p
         }
+        if (tid == 0 && P.bpf > 0) {
+            // b of plane q (rows y0-1 .. y0+TY) is loaded at the end of step q-1
+            const int q = p + 1 + P.bpf;
+            if (q >= 0 && q <= min(z1, P.NZ - 1)) {
+                const long long lo = (long long)q * P.S2 + gbase + S1, nn = (long long)P.NZ * P.S2;
+                bulk_prefetch_l2(P.b, max(lo, 0ll), min(lo + (long long)(P.TY + 2) * S1, nn));
+            }
+        }
     }
 }
 
@@ -2612,6 +2664,7 @@ static bool jr3_params(Level &L, Jr3 *P) {
     P->cS = B.coef[4];
     P->cP = B.coef[5];
     P->dsum = B.diag + B.coef[3] + B.coef[4];
+    P->bpf = env_int("OMG_BPF", 2);
     {   // z-segments of even length: 3 extra steps + ~1.5 planes of pipeline ramp per segment against whole waves of
         // one CTA per SM
         int chunks = NY / TY, slots = std::max(g.sm_count, 1);
