@@ -176,6 +176,9 @@ __device__ __forceinline__ void st_pull_arrive(const St3 &P, unsigned long long 
 // MODE 1: rc = R (b - A xi)
 // MODE 2: y = xi + R^T e ; xo = y + omega (b - A y)/d
 // MODE 3: xo = omega b/diag (first Jacobi sweep from x = 0) ; rc = R (b - A xo)      [xi == b]
+// MODE 4: the same for a uniform diagonal: x = (omega/d) b needs no transform pass — the 7-point pass runs on the staged
+//         b planes and its result is scaled (no second barrier per plane, b is not loaded a second time): level 1 of the
+//         512^3 hierarchy 0.105 -> 0.070 ms
 // PULL: the fused-halo-pull instantiation (slab levels); the single-GPU instantiation carries none of its code — the
 // prolong+Jacobi kernel loses 15 % when merely compiled with it (0.57 -> 0.65 ms at 512^3).
 template <int MODE, int NT, bool CLS, bool PULL>
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
         double2 ba[ST_PPT], bb[ST_PPT];
 #pragma unroll
         for (int k = 0; k < ST_PPT; ++k) {
-            if (act[k]) {
+            if (MODE != 4 && act[k]) {
                 int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
                 ba[k] = ldg2(P.b + gi);
                 bb[k] = ldg2(P.b + gi + P.S1);
@@ -432,12 +435,20 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                 if (cyb + cxy != 4) ax3 += corr(cyb + cxy, ob + 1);
             }
             const int gi = z * P.S2 + (y0 + 2 * py[k]) * P.S1 + 2 * px[k];
-            if (MODE == 1 || MODE == 3) {
+            if (MODE == 1 || MODE == 3 || MODE == 4) {
                 double a = acc[k];
-                a += ba[k].x - ax0;
-                a += ba[k].y - ax1;
-                a += bb[k].x - ax2;
-                a += bb[k].y - ax3;
+                if (MODE == 4) {
+                    // the staged planes hold b and x = (omega/d) b everywhere: A x = (omega/d) (A b)
+                    a += va.x - P.wod * ax0;
+                    a += va.y - P.wod * ax1;
+                    a += vb.x - P.wod * ax2;
+                    a += vb.y - P.wod * ax3;
+                } else {
+                    a += ba[k].x - ax0;
+                    a += ba[k].y - ax1;
+                    a += bb[k].x - ax2;
+                    a += bb[k].y - ax3;
+                }
                 if (z & 1) {
                     int Z = z >> 1;
                     P.rc[((long long)Z * P.cs1 + (y0 >> 1) + py[k]) * P.cs2 + px[k]] = P.w * a;
@@ -447,6 +458,10 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_st3(const St3 P) {
                 if (MODE == 3) {
                     *reinterpret_cast<double2 *>(P.xo + gi) = va;
                     *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = vb;
+                }
+                if (MODE == 4) {
+                    *reinterpret_cast<double2 *>(P.xo + gi) = make_double2(P.wod * va.x, P.wod * va.y);
+                    *reinterpret_cast<double2 *>(P.xo + gi + P.S1) = make_double2(P.wod * vb.x, P.wod * vb.y);
                 }
             } else {
                 double2 oa2, ob2;
@@ -1365,8 +1380,11 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
     static bool attr_set[2] = {false, false};
     size_t smem = st3_smem(P);
     if (smem > 227 * 1024) return false;
-    void (*kern)(const St3) = SPLIT ? k_st3x<MODE, 256>
-                                    : (P.use_cls ? k_st3<MODE, NT, true, false> : k_st3<MODE, NT, false, false>);
+    void (*kern)(const St3);
+    if constexpr (SPLIT)
+        kern = k_st3x<MODE, 256>;
+    else
+        kern = P.use_cls ? k_st3<MODE, NT, true, false> : k_st3<MODE, NT, false, false>;
     if (!attr_set[P.use_cls ? 1 : 0]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             cudaGetLastError();
@@ -1446,7 +1464,11 @@ static bool st3_launch_nt(omg_hierarchy *h, St3 P) {
 
 template <int MODE>
 static bool st3_launch(omg_hierarchy *h, const St3 &P, int NT) {
-    if (P.XH) return NT == 256 ? st3_launch_nt<MODE, 256, true>(h, P) : false;     // split rows: 256-thread CTAs only
+    if constexpr (MODE == 4) {
+        if (P.XH) return false;        // (no split-row instantiation of MODE 4)
+    } else {
+        if (P.XH) return NT == 256 ? st3_launch_nt<MODE, 256, true>(h, P) : false;     // split rows: 256-thread CTAs only
+    }
     if (NT == 128) return st3_launch_nt<MODE, 128, false>(h, P);
     if (NT == 256) return st3_launch_nt<MODE, 256, false>(h, P);
     return st3_launch_nt<MODE, 512, false>(h, P);
@@ -1767,7 +1789,11 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         P.has_exc = 1;       // per-row a_ii lookups in the transform (slow path; not hit by Poisson hierarchies)
         P.exc = L.exc_op();
     }
-    if (!st3_launch<3>(h, P, NT)) return false;
+    if (!P.has_exc && !P.XH && !getenv("OMG_NO_MODE4")) {        // (read per call: the parity test runs both)
+        if (!st3_launch<4>(h, P, NT)) return false;
+    } else if (!st3_launch<3>(h, P, NT)) {
+        return false;
+    }
     // fix-up: x_j = omega b_j / d is recomputed from b when the diagonal is uniform (x's halos are not filled yet)
     if (!P.use_cls) fix_crows(L, xo, b, rcv, L.exc_diag_uniform ? P.wod : 0.0);
     return true;
@@ -2506,24 +2532,39 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
     const bool hwrap = hwhich ? (y0 + P.TY == P.NY) : (y0 == 0);
     const int hshift = hwrap ? (hwhich ? 1 : -1) : 0;     // the plane the halo row really belongs to: p + hshift
 
-    // carried from plane to plane, per slot: the raw patch of plane p-1 (z- neighbours of pass A), the patch sums of
-    // the mid planes p-1 and p-2 and of b on plane p-1 (pass B), the b patch of plane p (fetched one step ahead),
-    // the residual sum of the open aggregate.
-    double2 za[JR3_PPT], zb[JR3_PPT], ba[JR3_PPT], bb[JR3_PPT];
-    double s1[JR3_PPT], s2[JR3_PPT], sb[JR3_PPT], acc[JR3_PPT];
-    double2 hz = make_double2(0.0, 0.0), hb = make_double2(0.0, 0.0);
+    // carried from plane to plane, per slot: the raw patches of the planes p-1 and p (z- neighbours and centres of pass
+    // A: the patch of plane p+1 is read from its staged plane once and moves down), the b patch of plane p (fetched one
+    // step ahead), and for pass B the patch sum S(p-1), the part of the residual sum of plane p-1 that was known when
+    // its mid patch was formed, and the residual sum of the open aggregate.
+    // The shared-memory pipe is what limits this kernel (ncu, first version, which re-read the patch of plane p from its
+    // staged plane: l1tex 72 %, short-scoreboard stalls on top): carrying it took the level-0 pass at 512^3 from 0.62 to
+    // 0.58 ms.  Fetching the x-neighbours of a patch — the neighbouring lanes' own values — by warp shuffle instead of
+    // the 2-way bank-conflicted LDS.64 was measured too and LOST (0.66 ms): the shuffles sit on the dependency chain in
+    // front of the FMAs.
+    double2 za[JR3_PPT], zb[JR3_PPT], ca[JR3_PPT], cb[JR3_PPT], ba[JR3_PPT], bb[JR3_PPT];
+    double s1[JR3_PPT], part[JR3_PPT], acc[JR3_PPT];
+    double2 hz = make_double2(0.0, 0.0), hc = hz, hb = hz;
 #pragma unroll
     for (int k = 0; k < JR3_PPT; ++k) {
-        za[k] = zb[k] = ba[k] = bb[k] = make_double2(0.0, 0.0);
-        s1[k] = s2[k] = sb[k] = acc[k] = 0.0;
+        za[k] = zb[k] = ca[k] = cb[k] = ba[k] = bb[k] = make_double2(0.0, 0.0);
+        s1[k] = part[k] = acc[k] = 0.0;
     }
 
-    if (z0 - 2 >= pfirst) wait_plane(z0 - 2);
-    // step z0-2 only fills the register pipeline (raw patch of plane z0-2, b of plane z0-1)
+    if (z0 - 2 >= pfirst) {
+        wait_plane(z0 - 2);
+        const double *rawf = raw + (size_t)slot_of(z0 - 2) * RS;
+#pragma unroll
+        for (int k = 0; k < JR3_PPT; ++k) {
+            if (k >= nslots) continue;
+            ca[k] = lds2(rawf + ro + k * KS);
+            cb[k] = lds2(rawf + ro + k * KS + S1);
+        }
+        if (hact) hc = lds2(rawf + ho);
+    }
+    // step z0-2 only fills the register pipeline (raw patches of the planes z0-2 and z0-1, b of plane z0-1)
     for (int p = z0 - 2; p <= z1; ++p) {
         const bool real = p >= z0 - 1;
         const bool relax = real && p >= 0 && p < P.NZ;
-        const bool has_cur = (p >= pfirst && p <= plast);
         const bool has_next = (p + 1 >= pfirst && p + 1 <= plast);
         if (has_next) wait_plane(p + 1);
         const double *rawc = raw + (size_t)slot_of(max(p, pfirst)) * RS;
@@ -2540,19 +2581,15 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
         for (int k = 0; k < JR3_PPT; ++k) {
             if (k >= nslots) continue;
             const int o = ro + k * KS;
-            double2 ra = make_double2(0.0, 0.0), rb = ra;
-            if (has_cur) {
-                ra = lds2(rawc + o);
-                rb = lds2(rawc + o + S1);
+            const double2 ra = ca[k], rb = cb[k];
+            double2 pa = make_double2(0.0, 0.0), pb = pa;
+            if (has_next) {
+                pa = lds2(rawn + o);
+                pb = lds2(rawn + o + S1);
             }
             double2 na = ra, nb = rb;
             if (relax) {
                 // ---- pass A
-                double2 pa = make_double2(0.0, 0.0), pb = pa;
-                if (has_next) {
-                    pa = lds2(rawn + o);
-                    pb = lds2(rawn + o + S1);
-                }
                 const double2 vn = lds2(rawc + o - S1), vs = lds2(rawc + o + 2 * S1);
                 const double la = rawc[o - 1], rra = rawc[o + 2], lb = rawc[o + S1 - 1], rrb = rawc[o + S1 + 2];
                 na.x = jr3_relax(P, ra.x, la, ra.y, vn.x, rb.x, za[k].x, pa.x, ba[k].x);
@@ -2571,23 +2608,29 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
             }
             const double s0 = (na.x + na.y) + (nb.x + nb.y);
             if (doB) {
-                // ---- pass B: patch sum of the residual of plane p-1
+                // ---- pass B, second half: what the residual sum of plane p-1 still lacks — the rows above and below
+                // the patch and the columns left and right of it (other threads' values: mid plane p-1), S(p)
                 const double2 mn = lds2(midp + o - S1), ms = lds2(midp + o + 2 * S1);
                 const double ml = midp[o - 1] + midp[o + S1 - 1], mr = midp[o + 2] + midp[o + S1 + 2];
-                const double ax = P.dsum * s1[k] + P.c1 * (ml + mr) + P.cS * ((mn.x + mn.y) + (ms.x + ms.y)) +
-                                  P.cP * (s2[k] + s0);
-                double a = acc[k] + (sb[k] - ax);
+                const double rest = P.c1 * (ml + mr) + P.cS * ((mn.x + mn.y) + (ms.x + ms.y)) + P.cP * s0;
+                double a = acc[k] + (part[k] - rest);
                 if ((p - 1) & 1) {
                     P.rc[((long long)((p - 1) >> 1) * P.cs1 + (y0 >> 1) + pj + k * (NT / HX)) * P.cs2 + pi_] = P.w * a;
                     a = 0.0;
                 }
                 acc[k] = a;
             }
-            s2[k] = s1[k];
+            {
+                // ---- pass B, first half, for plane p: everything known while its mid patch is in registers — the b
+                // sum, the own patch, S(p-1)
+                const double sbk = (ba[k].x + ba[k].y) + (bb[k].x + bb[k].y);
+                part[k] = sbk - (P.dsum * s0 + P.cP * s1[k]);
+            }
             s1[k] = s0;
-            sb[k] = (ba[k].x + ba[k].y) + (bb[k].x + bb[k].y);
             za[k] = ra;
             zb[k] = rb;
+            ca[k] = pa;
+            cb[k] = pb;
             if (bnext) {
                 ba[k] = ldg2(bpn + o);
                 bb[k] = ldg2(bpn + o + S1);
@@ -2595,12 +2638,11 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
         }
         if (hact) {
             // the halo item's row may belong to the neighbouring plane: relaxed iff that point lies inside [0,n)
-            double2 hr = make_double2(0.0, 0.0);
-            if (has_cur) hr = lds2(rawc + ho);
+            const double2 hr = hc;
+            double2 hp = make_double2(0.0, 0.0);
+            if (has_next) hp = lds2(rawn + ho);
             double2 hm = hr;
             if (real && p + hshift >= 0 && p + hshift < P.NZ) {
-                double2 hp = make_double2(0.0, 0.0);
-                if (has_next) hp = lds2(rawn + ho);
                 const double2 hn = lds2(rawc + ho - S1), hs = lds2(rawc + ho + S1);
                 const double hl = rawc[ho - 1], hrr = rawc[ho + 2];
                 hm.x = jr3_relax(P, hr.x, hl, hr.y, hn.x, hs.x, hz.x, hp.x, hb.x);
@@ -2608,6 +2650,7 @@ __global__ void __launch_bounds__(JR3_NT, 1) k_jr3(const Jr3 P) {
             }
             if (real) sts2(midw + ho, hm);
             hz = hr;
+            hc = hp;
             if (p + 1 >= z0 - 1 && p + 1 <= z1 && p + 1 + hshift >= 0 && p + 1 + hshift < P.NZ)
                 hb = ldg2(P.b + (long long)(p + 1) * P.S2 + gbase + ho);
         }

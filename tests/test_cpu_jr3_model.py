@@ -5,7 +5,9 @@ The CUDA kernel marches in z over full-row chunks: pass A(p) relaxes every point
 p-1, p, p+1 into a "mid" plane (and stores the planes the segment owns), pass B(p-1) forms the PATCH SUM of the
 residual of plane p-1 from the mid planes p-2, p-1, p —
     sum_patch (A x) = (d + c1 + cS) S(p-1) + c1 (left + right columns) + cS (row above + row below) + cP (S(p-2) + S(p))
-— and accumulates it over the plane pair of the aggregate.  Halo rows y0-1 / y0+TY and halo planes z0-1 / z1 are
+— in two halves (what is known while the mid patch of plane p-1 is still in registers; the rest one step later from
+shared memory) and accumulates it over the plane pair of the aggregate.  The raw patches of the planes p-1 and p are
+carried in registers.  Halo rows y0-1 / y0+TY and halo planes z0-1 / z1 are
 recomputed, the 3-stage raw ring and the 2-plane mid ring are reused, rows outside [0,NY) are rows of the neighbouring
 plane (flat-index semantics, openmg/operators.py:244-256).  This file restates exactly that index logic thread by
 thread (threads run one after another between barriers; ring residency is asserted) and checks it against the oracle's
@@ -26,13 +28,17 @@ def jr3_model(NZ, NY, S1, NT, TY, ZL, seed=0):
     rs = np.random.RandomState(seed)
     x, b = rs.random_sample(n), rs.random_sample(n)
     omega = 0.8
-    d = A[S2 + S1 + 1, S2 + S1 + 1]; c1 = A[S2 + S1 + 1, S2 + S1 + 2]; cS = A[S2 + S1 + 1, S2 + 2 * S1 + 1]; cP = A[S2 + S1 + 1, 2 * S2 + S1 + 1]
-    wod = omega / d; dsum = d + c1 + cS
+    i = S2 + S1 + 1
+    d, c1, cS, cP = A[i, i], A[i, i + 1], A[i, i + S1], A[i, i + S2]
+    wod = omega / d
+    dsum = d + c1 + cS
     R = orc.restrictionList(shape, 1, 2)[0]
     w = R.data[0]
     pad = S2 + 2 * S1
-    X = np.zeros(n + 2 * pad); X[pad:pad + n] = x
-    B = np.zeros(n + 2 * pad); B[pad:pad + n] = b
+    X = np.zeros(n + 2 * pad)
+    X[pad:pad + n] = x
+    B = np.zeros(n + 2 * pad)
+    B[pad:pad + n] = b
     XO = np.zeros(n + 2 * pad)
     cs1, cs2 = NY // 2, S1 // 2
     RC = np.full(n // 8, np.nan)
@@ -41,94 +47,138 @@ def jr3_model(NZ, NY, S1, NT, TY, ZL, seed=0):
     NS, NM, KS = 3, 2, 4 * NT
     nslots = ((TY // 2) * HX) // NT
     assert nslots in (1, 2) and ((TY // 2) * HX) % NT == 0 and S1 <= NT and NT % HX == 0
+
     def relaxf(c, l, r, nn, s, zm, zp, bv):
         ax = d * c + c1 * (l + r) + cS * (nn + s) + cP * (zm + zp)
         return c + wod * (bv - ax)
+
+    Z2 = lambda: np.zeros(2)
     for by in range((NZ + ZL - 1) // ZL):
-      for bx in range(NY // TY):
-        y0 = bx * TY; z0 = by * ZL; z1 = min(z0 + ZL, NZ)
-        pfirst = max(z0 - 2, -1); plast = min(z1 + 1, NZ)
-        gbase = (y0 - 2) * S1
-        raw = {}    # plane -> staged array (emulate ring by checking residency)
-        resident = set()
-        def stage(p):
-            raw[p] = X[pad + p * S2 + gbase: pad + p * S2 + gbase + RS].copy(); resident.add(p)
-        for p in range(pfirst, min(pfirst + NS, plast + 1)): stage(p)
-        mid = [np.full(MS, np.nan) for _ in range(NM)]
-        st = [dict(za=[np.zeros(2)] * 2, zb=[np.zeros(2)] * 2, ba=[np.zeros(2)] * 2, bb=[np.zeros(2)] * 2, s1=[0.0] * 2, s2=[0.0] * 2,
-                   sb=[0.0] * 2, acc=[0.0] * 2, hz=np.zeros(2), hb=np.zeros(2)) for _ in range(NT)]
-        for p in range(z0 - 2, z1 + 1):
-            real = p >= z0 - 1; relax = real and 0 <= p < NZ
-            has_cur = pfirst <= p <= plast; has_next = pfirst <= p + 1 <= plast
-            if has_cur: assert p in resident
-            if has_next: assert p + 1 in resident
-            rawc = raw.get(p); rawn = raw.get(p + 1)
-            mq = p - z0 + 2 + NM
-            midw = mid[mq % NM]; midp = mid[(mq - 1) % NM]      # index with offset - S1
-            owned = z0 <= p < z1; doB = p - 1 >= z0
-            bnext = (p + 1 >= max(z0 - 1, 0)) and (p + 1 <= min(z1, NZ - 1))
+        for bx in range(NY // TY):
+            y0, z0 = bx * TY, by * ZL
+            z1 = min(z0 + ZL, NZ)
+            pfirst, plast = max(z0 - 2, -1), min(z1 + 1, NZ)
+            gbase = (y0 - 2) * S1
+            raw = {}            # resident staged planes (the ring: at most NS, refilled after the barrier)
+
+            def stage(q):
+                assert len(raw) < NS
+                raw[q] = X[pad + q * S2 + gbase: pad + q * S2 + gbase + RS].copy()
+            for q in range(pfirst, min(pfirst + NS, plast + 1)):
+                stage(q)
+            mid = [np.full(MS, np.nan) for _ in range(NM)]
+            st = [dict(za=[Z2(), Z2()], zb=[Z2(), Z2()], ca=[Z2(), Z2()], cb=[Z2(), Z2()], ba=[Z2(), Z2()],
+                       bb=[Z2(), Z2()], s1=[0.0] * 2, part=[0.0] * 2, acc=[0.0] * 2, hz=Z2(), hc=Z2(), hb=Z2())
+                  for _ in range(NT)]
+            geo = []
             for tid in range(NT):
-                T = st[tid]
                 pj, pi_ = divmod(tid, HX)
-                ro = (2 * pj + 2) * S1 + 2 * pi_
+                hwhich = tid >= HX
+                ho = (TY + 2) * S1 + 2 * (tid - HX) if hwhich else S1 + 2 * tid
+                hwrap = (y0 + TY == NY) if hwhich else (y0 == 0)
+                geo.append((pj, pi_, (2 * pj + 2) * S1 + 2 * pi_, ho, ((1 if hwhich else -1) if hwrap else 0)))
+            if z0 - 2 >= pfirst:
+                rawf = raw[z0 - 2]
+                for tid in range(NT):
+                    ro, ho = geo[tid][2], geo[tid][3]
+                    for k in range(nslots):
+                        st[tid]['ca'][k] = rawf[ro + k * KS:ro + k * KS + 2].copy()
+                        st[tid]['cb'][k] = rawf[ro + k * KS + S1:ro + k * KS + S1 + 2].copy()
+                    if tid < 2 * HX:
+                        st[tid]['hc'] = rawf[ho:ho + 2].copy()
+            for p in range(z0 - 2, z1 + 1):
+                real = p >= z0 - 1
+                relax = real and 0 <= p < NZ
+                has_next = pfirst <= p + 1 <= plast
+                if relax:
+                    assert p in raw
+                if has_next:
+                    assert p + 1 in raw
+                rawc, rawn = raw.get(p), raw.get(p + 1)
+                mq = p - z0 + 2 + NM
+                midw, midp = mid[mq % NM], mid[(mq - 1) % NM]          # staged-row offsets: index - S1
+                owned, doB = z0 <= p < z1, p - 1 >= z0
+                bnext = (p + 1 >= max(z0 - 1, 0)) and (p + 1 <= min(z1, NZ - 1))
                 for k in range(nslots):
-                    o = ro + k * KS
-                    ra = rawc[o:o + 2].copy() if has_cur else np.zeros(2)
-                    rb = rawc[o + S1:o + S1 + 2].copy() if has_cur else np.zeros(2)
-                    na, nb = ra.copy(), rb.copy()
-                    if relax:
-                        pa = rawn[o:o + 2] if has_next else np.zeros(2)
-                        pb = rawn[o + S1:o + S1 + 2] if has_next else np.zeros(2)
-                        vn = rawc[o - S1:o - S1 + 2]; vs = rawc[o + 2 * S1:o + 2 * S1 + 2]
-                        la, rra, lb, rrb = rawc[o - 1], rawc[o + 2], rawc[o + S1 - 1], rawc[o + S1 + 2]
-                        za, zb, ba, bb = T['za'][k], T['zb'][k], T['ba'][k], T['bb'][k]
-                        na[0] = relaxf(ra[0], la, ra[1], vn[0], rb[0], za[0], pa[0], ba[0])
-                        na[1] = relaxf(ra[1], ra[0], rra, vn[1], rb[1], za[1], pa[1], ba[1])
-                        nb[0] = relaxf(rb[0], lb, rb[1], ra[0], vs[0], zb[0], pb[0], bb[0])
-                        nb[1] = relaxf(rb[1], rb[0], rrb, ra[1], vs[1], zb[1], pb[1], bb[1])
-                        if owned:
-                            gi = pad + p * S2 + gbase + o
-                            XO[gi:gi + 2] = na; XO[gi + S1:gi + S1 + 2] = nb
-                    if real:
-                        midw[o - S1:o - S1 + 2] = na; midw[o:o + 2] = nb
-                    s0 = (na[0] + na[1]) + (nb[0] + nb[1])
-                    if doB:
-                        m = lambda off: midp[off - S1]
-                        mn = m(o - S1) + m(o - S1 + 1); ms = m(o + 2 * S1) + m(o + 2 * S1 + 1)
-                        ml = m(o - 1) + m(o + S1 - 1); mr = m(o + 2) + m(o + S1 + 2)
-                        ax = dsum * T['s1'][k] + c1 * (ml + mr) + cS * (mn + ms) + cP * (T['s2'][k] + s0)
-                        a = T['acc'][k] + (T['sb'][k] - ax)
-                        if (p - 1) & 1:
-                            RC[(((p - 1) >> 1) * cs1 + (y0 >> 1) + pj + k * (NT // HX)) * cs2 + pi_] = w * a
-                            a = 0.0
-                        T['acc'][k] = a
-                    T['s2'][k] = T['s1'][k]; T['s1'][k] = s0
-                    T['sb'][k] = (T['ba'][k][0] + T['ba'][k][1]) + (T['bb'][k][0] + T['bb'][k][1])
-                    T['za'][k] = ra; T['zb'][k] = rb
-                    if bnext:
-                        gi = pad + (p + 1) * S2 + gbase + o
-                        T['ba'][k] = B[gi:gi + 2].copy(); T['bb'][k] = B[gi + S1:gi + S1 + 2].copy()
-                if tid < 2 * HX:
-                    hwhich = tid >= HX
-                    ho = (TY + 2) * S1 + 2 * (tid - HX) if hwhich else S1 + 2 * tid
-                    hwrap = (y0 + TY == NY) if hwhich else (y0 == 0)
-                    hshift = (1 if hwhich else -1) if hwrap else 0
-                    hr = rawc[ho:ho + 2].copy() if has_cur else np.zeros(2)
+                    new = []
+                    for tid in range(NT):           # pass A
+                        T = st[tid]
+                        pj, pi_, ro, ho, hshift = geo[tid]
+                        o = ro + k * KS
+                        ra, rb = T['ca'][k], T['cb'][k]
+                        pa = rawn[o:o + 2].copy() if has_next else Z2()
+                        pb = rawn[o + S1:o + S1 + 2].copy() if has_next else Z2()
+                        na, nb = ra.copy(), rb.copy()
+                        if relax:
+                            vn, vs = rawc[o - S1:o - S1 + 2], rawc[o + 2 * S1:o + 2 * S1 + 2]
+                            la, lb, rra, rrb = rawc[o - 1], rawc[o + S1 - 1], rawc[o + 2], rawc[o + S1 + 2]
+                            za, zb, ba, bb = T['za'][k], T['zb'][k], T['ba'][k], T['bb'][k]
+                            na[0] = relaxf(ra[0], la, ra[1], vn[0], rb[0], za[0], pa[0], ba[0])
+                            na[1] = relaxf(ra[1], ra[0], rra, vn[1], rb[1], za[1], pa[1], ba[1])
+                            nb[0] = relaxf(rb[0], lb, rb[1], ra[0], vs[0], zb[0], pb[0], bb[0])
+                            nb[1] = relaxf(rb[1], rb[0], rrb, ra[1], vs[1], zb[1], pb[1], bb[1])
+                            if owned:
+                                gi = pad + p * S2 + gbase + o
+                                XO[gi:gi + 2] = na
+                                XO[gi + S1:gi + S1 + 2] = nb
+                        if real:
+                            midw[o - S1:o - S1 + 2] = na
+                            midw[o:o + 2] = nb
+                        new.append((na, nb, pa, pb))
+                    for tid in range(NT):           # pass B
+                        T = st[tid]
+                        pj, pi_, ro, ho, hshift = geo[tid]
+                        o = ro + k * KS
+                        na, nb, pa, pb = new[tid]
+                        s0 = (na[0] + na[1]) + (nb[0] + nb[1])
+                        if doB:
+                            m = lambda off: midp[off - S1]
+                            mn, ms = m(o - S1) + m(o - S1 + 1), m(o + 2 * S1) + m(o + 2 * S1 + 1)
+                            ml, mr = m(o - 1) + m(o + S1 - 1), m(o + 2) + m(o + S1 + 2)
+                            rest = c1 * (ml + mr) + cS * (mn + ms) + cP * s0
+                            a = T['acc'][k] + (T['part'][k] - rest)
+                            if (p - 1) & 1:
+                                RC[(((p - 1) >> 1) * cs1 + (y0 >> 1) + pj + k * (NT // HX)) * cs2 + pi_] = w * a
+                                a = 0.0
+                            T['acc'][k] = a
+                        sbk = (T['ba'][k][0] + T['ba'][k][1]) + (T['bb'][k][0] + T['bb'][k][1])
+                        T['part'][k] = sbk - (dsum * s0 + cP * T['s1'][k])
+                        T['s1'][k] = s0
+                    for tid in range(NT):           # register rotation, b of plane p+1
+                        T = st[tid]
+                        o = geo[tid][2] + k * KS
+                        T['za'][k], T['zb'][k] = T['ca'][k], T['cb'][k]
+                        T['ca'][k], T['cb'][k] = new[tid][2], new[tid][3]
+                        if bnext:
+                            gi = pad + (p + 1) * S2 + gbase + o
+                            T['ba'][k] = B[gi:gi + 2].copy()
+                            T['bb'][k] = B[gi + S1:gi + S1 + 2].copy()
+                hnew = {}
+                for tid in range(min(NT, 2 * HX)):  # halo items
+                    T = st[tid]
+                    pj, pi_, ro, ho, hshift = geo[tid]
+                    hr = T['hc']
+                    hp = rawn[ho:ho + 2].copy() if has_next else Z2()
                     hm = hr.copy()
                     if real and 0 <= p + hshift < NZ:
-                        hp = rawn[ho:ho + 2] if has_next else np.zeros(2)
-                        hn = rawc[ho - S1:ho - S1 + 2]; hs = rawc[ho + S1:ho + S1 + 2]
+                        hn, hs = rawc[ho - S1:ho - S1 + 2], rawc[ho + S1:ho + S1 + 2]
                         hl, hrr = rawc[ho - 1], rawc[ho + 2]
                         hm[0] = relaxf(hr[0], hl, hr[1], hn[0], hs[0], T['hz'][0], hp[0], T['hb'][0])
                         hm[1] = relaxf(hr[1], hr[0], hrr, hn[1], hs[1], T['hz'][1], hp[1], T['hb'][1])
-                    if real: midw[ho - S1:ho - S1 + 2] = hm
-                    T['hz'] = hr
+                    if real:
+                        midw[ho - S1:ho - S1 + 2] = hm
+                    hnew[tid] = hp
+                for tid in range(min(NT, 2 * HX)):
+                    T = st[tid]
+                    ho, hshift = geo[tid][3], geo[tid][4]
+                    T['hz'], T['hc'] = T['hc'], hnew[tid]
                     if p + 1 >= z0 - 1 and p + 1 <= z1 and 0 <= p + 1 + hshift < NZ:
                         gi = pad + (p + 1) * S2 + gbase + ho
                         T['hb'] = B[gi:gi + 2].copy()
-            # barrier; refill
-            if p >= pfirst and p + NS <= plast:
-                resident.discard(p); raw.pop(p); stage(p + NS)
+                # barrier; thread 0 refills the slot of plane p
+                if p >= pfirst and p + NS <= plast:
+                    raw.pop(p)
+                    stage(p + NS)
     return A, R, x, b, omega, XO[pad:pad + n], RC
 
 

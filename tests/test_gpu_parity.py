@@ -280,6 +280,37 @@ def test_3d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, monkeypa
     assert np.abs(rg).max() <= 1e-12 * np.abs(bs).max(), "x already solves A x = b: restricted residual at rounding level"
 
 
+@pytest.mark.parametrize("shape,gl", [((64, 64, 64), 3), ((128, 32, 128), 3)])
+def test_zero_start_descent_with_and_without_transform_pass(shape, gl, monkeypatch):
+    """Levels >= 1 start from the zero iterate (openmg/__init__.py:191-192).  On levels with a uniform diagonal the
+    fused sweep + residual + restriction kernel runs its 7-point pass on the staged b planes and scales the result
+    (k_st3 MODE 4); OMG_NO_MODE4 selects the older form that first turns the staged planes into x = omega b / a_ii.
+    Both against the oracle's cycles and against each other."""
+    A_in = orc.poisson_csr(shape)
+    _, b = seeded_problem(A_in)
+    params = {'problemShape': shape, 'gridLevels': gl, 'preIterations': 1, 'postIterations': 1,
+              'verbose': False, 'minSize': 8}
+    R = orc.restrictionList(shape, gl - 1, 8)
+    params['coarsestLevel'] = len(R)
+    A = orc.coeffecientList(A_in, R)
+    smooth = orc.make_smoother("jacobi", shape, 0.8)
+    x = None
+    for _ in range(2):
+        x, info = orc.mgCycle(A, b, 0, R, params, initial=x, smooth=smooth)
+    outs = {}
+    for on in (False, True):
+        if on:
+            monkeypatch.delenv("OMG_NO_MODE4", raising=False)
+        else:
+            monkeypatch.setenv("OMG_NO_MODE4", "1")
+        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+        outs[on] = h.solve(b, None, 1, 1, "jacobi", 0.8, 2, 0.0)[0]
+        h.close()
+    close(outs[True], x, JAC_RTOL, "scaled 7-point pass on b vs oracle")
+    close(outs[False], x, JAC_RTOL, "transform pass vs oracle")
+    close(outs[True], outs[False], 1e-14, "both forms")
+
+
 def test_band_detection_reports_structure():
     h = Hierarchy(orc.poisson_csr((32, 32, 32)), (32, 32, 32), 2, 8)
     i0, i1 = h.level_info(0), h.level_info(1)
