@@ -1362,8 +1362,8 @@ static bool st3_params(Level &L, St3 *P, int *NT_out, bool xf) {
     P->ZL = ZL;
     P->has_exc = 0;
     P->colour = -1;
-    P->bpf = env_int("OMG_BPF", 2);
-    P->epf = env_int("OMG_EPF", 4);
+    P->bpf = L.slab ? 0 : env_int("OMG_BPF", 2);      // (slab levels: the sharded kernels are left as measured at 2-8 ranks)
+    P->epf = L.slab ? 0 : env_int("OMG_EPF", 4);
     P->use_cls = 0;
     if (L.kind == OMG_KIND_BAND_EXC && L.classed && XH == 0) {
         P->use_cls = 1;
@@ -1789,7 +1789,7 @@ bool stencil_jacobi0_residual_restrict(omg_hierarchy *h, Level &L, Level &C, con
         P.has_exc = 1;       // per-row a_ii lookups in the transform (slow path; not hit by Poisson hierarchies)
         P.exc = L.exc_op();
     }
-    if (!P.has_exc && !P.XH && !getenv("OMG_NO_MODE4")) {        // (read per call: the parity test runs both)
+    if (!P.has_exc && !P.XH && !L.slab && !getenv("OMG_NO_MODE4")) {        // (read per call: the parity test runs both)
         if (!st3_launch<4>(h, P, NT)) return false;
     } else if (!st3_launch<3>(h, P, NT)) {
         return false;

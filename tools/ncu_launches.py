@@ -53,9 +53,10 @@ def main():
         # dominant kernel up under the workload shape ({"<shape>": {"<name>@L0": DRAM bytes per launch}, "source": ..})
         shape = sys.argv[sys.argv.index("--shape") + 1] if "--shape" in sys.argv else "512x512x512"
         smoother = sys.argv[sys.argv.index("--smoother") + 1] if "--smoother" in sys.argv else "jacobi"
-        names = {"jacobi": ["jacobi@L0", "residual_restrict@L0", "prolong_jacobi@L0"],
+        # (Jacobi: the pre-smoothing sweep and the restricted residual are one launch, k_jr3)
+        names = {"jacobi": ["jacobi_residual_restrict@L0", "prolong_jacobi@L0"],
                  "rbgs": ["rbgs_sweep@L0", "residual_restrict@L0", "prolong_rbgs_sweep@L0"]}[smoother]
-        sel = [rows[0], rows[1], rows[-1]]
+        sel = [rows[0], rows[-1]] if smoother == "jacobi" else [rows[0], rows[1], rows[-1]]
         try:
             out = json.load(open(traffic_out))
             if not isinstance(out.get(shape, {}), dict) or "source" not in out:
