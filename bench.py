@@ -294,6 +294,11 @@ def ours(args):
     with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as cs:
         rep_ms, launches = timed_cycles(h, args, args.smoother, barrier, allmax, args.reps)
         ms = min(rep_ms)
+        # per-kernel shares (CUDA events around every launch of 3 directly launched cycles), taken right behind the timed
+        # repetitions: under the power cap a B200 slows by several per cent within the first second of sustained load
+        # (see `repetitions_ms_per_step`), so a profile taken after the filler below would describe a hotter GPU than
+        # the one `value` was measured on
+        prof = h.profile_cycle(3, args.pre, args.post, args.smoother, 0.8)
         if sum(rep_ms) < 1500:   # keep the GPU under the same load a little longer so the sampler sees it
             h.bench_cycles(max(args.steps, int(1500 / max(ms / args.steps, 1e-3))), args.pre, args.post,
                            args.smoother, 0.8)
@@ -325,8 +330,7 @@ def ours(args):
                         "fused_frac_of_measured_peak": fach / peak})
         return out
 
-    # ---- per-kernel shares (CUDA events, direct launches) and the roofline of the dominant kernel
-    prof = h.profile_cycle(3, args.pre, args.post, args.smoother, 0.8)
+    # ---- the roofline of the dominant kernel
     tot = sum(p["ms"] * p["launches"] / 3.0 for p in prof)
     dom = max(prof, key=lambda p: p["ms"] * p["launches"] if p["bytes"] > 0 else 0.0)
     ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
