@@ -1,5 +1,5 @@
 """Workload for compute-sanitizer (tools/sanitize.sh): every structured kernel family once, on the smallest shapes
-that still select them — the TMA/mbarrier rings of k_st3 / k_st2 / k_st2rb / k_rb3 (plain and prolongation-fused,
+that still select them — the TMA/mbarrier rings of k_st3 / k_st2 / k_st2rb / k_rb3 / k_jr3 (plain and prolongation-fused,
 band and class-corrected levels) and whole V-cycles with both smoothers, direct launches (no CUDA graph)."""
 import os
 import sys
@@ -24,6 +24,7 @@ for shape, gl in cases:
         h.smooth(l, b, x, 1, "jacobi", 0.8)
         h.smooth(l, b, x, 1, "rbgs")
         h.residual_restrict(l, b, x)
+        h.smooth_residual_restrict(l, b, x, 1, "jacobi", 0.8)      # level 0: k_jr3 (sweep + residual + restriction)
         h.prolong_correct_smooth(l, b, e, x, 1, "jacobi", 0.8)
         h.prolong_correct_smooth(l, b, e, x, 1, "rbgs")
         h.residual_norm(l, b, x)
