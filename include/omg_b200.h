@@ -200,7 +200,7 @@ int omg_smooth_to_threshold(omg_hierarchy *h, int level, const double *b_host, d
 int omg_residual_restrict(omg_hierarchy *h, int level, const double *b_host, const double *x_host, double *rc_host);
 /* The descent step of mgCycle on one level (openmg/__init__.py:201 pre-smoothing, :209-210 residual + restriction):
  * x := smooth(A_l, b, x, sweeps) in/out, rc := R_l (b - A_l x) with n_{l+1} entries.  The last Jacobi sweep and the
- * restricted residual run as one pass over x where the level allows it (k_jr3). */
+ * restricted residual run as one pass over x where the level allows it (k_jr3 / k_jr2). */
 int omg_smooth_residual_restrict(omg_hierarchy *h, int level, const double *b_host, double *x_host, int sweeps,
                                  int smoother, double omega, double *rc_host);
 /* x += R_l^T e   (openmg/__init__.py:214,224) */

@@ -1193,6 +1193,159 @@ __global__ void __launch_bounds__(ST2_NT, 2) k_st2rb(const St2 P) {
     }
 }
 
+// ================================================================ 2-D / 1-D Jacobi sweep + residual + restriction in one pass
+//
+// k_jr3 one dimension down, on the skeleton of k_st2rb (x-chunks of y-segments, marching over rows; one TMA bulk copy
+// per raw row with 4 halo columns per side from the FLAT vector, ring of NS stages; 3 de-interleaved mid rows):
+//   pass A(it)   Jacobi on every point of row `it` from the raw rows it-1, it, it+1 -> mid row `it` (and, for the rows
+//                and columns the CTA owns, the new iterate in global memory); it also runs on one halo pair per side
+//                and on the rows y0-1 and y1 (recomputed, never stored)
+//   pass B(it-1) residual of row it-1 from the mid rows it-2, it-1, it, summed over the x-pair and (2-D) the row pair
+//                of the aggregate -> one coarse value
+// x and b are read once: 24 n + 8 n_c bytes instead of 24 n + (16 n + 8 n_c).  Pure-band, unsharded levels (level 0 of
+// the 2-D / 1-D Poisson hierarchies: openmg/operators.py:191-241); 1-D vectors are viewed as rows of N.
+#define JR2_PP 5           // pairs per thread per row, halo pairs included
+
+template <bool HASN>
+__global__ void __launch_bounds__(ST2_NT, 2) k_jr2(const St2 P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NT = ST2_NT;
+    const int NS = P.NS, RP = P.XW + 8, MP = P.XW + 4;
+    double *raw = reinterpret_cast<double *>(smem_raw);
+    double *mid = raw + (size_t)NS * RP;
+    uint64_t *full = reinterpret_cast<uint64_t *>(mid + 3 * MP);
+    const int tid = threadIdx.x;
+    const int x0 = (int)blockIdx.x * P.XW;
+    const int y0 = (int)blockIdx.y * P.YL;
+    const int y1 = min(y0 + P.YL, P.NY);
+    const int rlo = y0 - 2, rhi = y1 + 1;                           // staged raw rows
+    const int first = y0 - 1;                                       // first row pass A runs on
+    const long long ntot = (long long)P.NY * P.N;
+    const uint32_t row_bytes = (uint32_t)RP * 8u;
+
+    auto issue_row = [&](int r) {
+        int slot = (r - rlo) % NS;
+        mbar_expect_tx(full + slot, row_bytes);
+        bulk_g2s(raw + (size_t)slot * RP, P.xi + (long long)r * P.N + x0 - 4, row_bytes, full + slot);
+    };
+    auto wait_row = [&](int r) {
+        int q = r - rlo;
+        mbar_wait(full + (q % NS), (uint32_t)((q / NS) & 1));
+    };
+    auto raw_row = [&](int r) { return raw + (size_t)((r - rlo) % NS) * RP; };
+    auto mid_row = [&](int r) { return mid + (size_t)((r - (y0 - 1)) % 3) * MP; };
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int r = rlo; r < rlo + NS && r <= rhi; ++r) issue_row(r);
+
+    const int HXW = P.XW >> 1;
+    const int NPA = HXW + 2;         // pass-A pairs: pair p covers columns x0 - 2 + 2p, +1
+    const int MPH = MP >> 1;         // pairs per mid row
+
+    double2 bold[JR2_PP];            // b of row it-1
+    double acc[JR2_PP];              // residual sum of the open aggregate
+#pragma unroll
+    for (int k = 0; k < JR2_PP; ++k) {
+        bold[k] = make_double2(0.0, 0.0);
+        acc[k] = 0.0;
+    }
+
+    for (int it = y0 - 1; it <= y1; ++it) {
+        double *mw = mid_row(it);
+        double2 bv[JR2_PP];
+#pragma unroll
+        for (int k = 0; k < JR2_PP; ++k) {
+            int p = tid + k * NT;
+            bv[k] = make_double2(0.0, 0.0);
+            if (p < NPA) bv[k] = ldg2(P.b + (long long)it * P.N + x0 - 2 + 2 * p);
+        }
+        if (it == first) {
+            wait_row(it - 1);
+            wait_row(it);
+        }
+        wait_row(it + 1);
+        {
+            // ---- pass A
+            const double *sm = raw_row(it - 1), *sc = raw_row(it), *sp = raw_row(it + 1);
+            const bool own_row = it >= y0 && it < y1;
+#pragma unroll
+            for (int k = 0; k < JR2_PP; ++k) {
+                int p = tid + k * NT;
+                if (p >= NPA) continue;
+                const int o = 2 + 2 * p;
+                const int xg = x0 - 2 + 2 * p;
+                const long long gi = (long long)it * P.N + xg;
+                double2 c = lds2(sc + o);
+                if (gi >= 0 && gi < ntot) {         // points outside the vector are never relaxed: they stay zero (pads)
+                    const double l = sc[o - 1], r = sc[o + 2];
+                    const double2 q = lds2(sp + o);
+                    const double ml = sm[o - 1], m0 = sm[o], pr = sp[o + 2];
+                    double ax0 = P.d * c.x + P.c1 * (l + c.y) + P.cD * (ml + q.y);
+                    double ax1 = P.d * c.y + P.c1 * (c.x + r) + P.cD * (m0 + pr);
+                    if (HASN) {
+                        ax0 += P.cN * (m0 + q.x);
+                        ax1 += P.cN * (sm[o + 1] + q.y);
+                    }
+                    c.x += P.wod * (bv[k].x - ax0);
+                    c.y += P.wod * (bv[k].y - ax1);
+                    if (own_row && p >= 1 && p <= HXW) *reinterpret_cast<double2 *>(P.xo + gi) = c;
+                }
+                // mid rows are stored de-interleaved (even elements, then odd elements): pass B reads them conflict-free
+                mw[p] = c.x;
+                mw[MPH + p] = c.y;
+            }
+        }
+        __syncthreads();        // mid row `it` complete
+        const int r = it - 1;
+        if (r >= y0) {
+            // ---- pass B
+            const double *em = mid_row(r - 1), *ec = mid_row(r), *ep = mid_row(r + 1);     // even elements of the pairs
+            const double *om = em + MPH, *oc = ec + MPH, *op = ep + MPH;                   // odd elements
+            const bool close_agg = P.oned || (r & 1);
+            double *rcrow = P.rc + (P.oned ? (long long)r : (long long)(r >> 1)) * P.cs + (x0 >> 1) - 1;
+#pragma unroll
+            for (int k = 0; k < JR2_PP; ++k) {
+                int p = tid + k * NT;
+                if (p < 1 || p > HXW) continue;
+                const double cx = ec[p], cy = oc[p];
+                double ax0 = P.d * cx + P.c1 * (oc[p - 1] + cy) + P.cD * (om[p - 1] + op[p]);
+                double ax1 = P.d * cy + P.c1 * (cx + ec[p + 1]) + P.cD * (em[p] + ep[p + 1]);
+                if (HASN) {
+                    ax0 += P.cN * (em[p] + ep[p]);
+                    ax1 += P.cN * (om[p] + op[p]);
+                }
+                double a = acc[k] + ((bold[k].x - ax0) + (bold[k].y - ax1));
+                if (close_agg) {
+                    rcrow[p] = P.w * a;
+                    a = 0.0;
+                }
+                acc[k] = a;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < JR2_PP; ++k) bold[k] = bv[k];
+        __syncthreads();        // raw row it-1 and mid row it-2 are free
+        if (tid == 0) {
+            int rn = it - 1 + NS;
+            if (rn <= rhi) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_row(rn);
+            }
+            const int yb = it + P.bpf;
+            if (P.bpf > 0 && yb >= 0 && yb <= y1 && yb < P.NY) {
+                const long long bo = (long long)yb * P.N + x0;
+                bulk_prefetch_l2(P.b, bo, bo + P.XW);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- fix-ups for exception rows
 
 // xo_i for exception rows, MODE 0 (jacobi) and MODE 2 (prolong + jacobi, y = x + R^T e on the fly).
@@ -2762,7 +2915,33 @@ bool stencil_jacobi_residual_restrict(omg_hierarchy *h, Level &L, Level &C, cons
                                       double *xo, double *rcv, double omega) {
     (void)C;
     Jr3 P{};
-    if (!jr3_params(L, &P)) return false;
+    if (!jr3_params(L, &P)) {
+        // 2-D / 1-D levels: k_jr2
+        St2 Q{};
+        if (getenv("OMG_NO_JR3") != nullptr || L.kind != OMG_KIND_BAND || L.slab) return false;
+        if (!st2_params(L, &Q, true, true) || (Q.XW + 4) / 2 > ST2_NT * JR2_PP) return false;
+        if (!xi) return true;
+        Q.xi = xi;
+        Q.b = b;
+        Q.xo = xo;
+        Q.rc = rcv + L.piece_row0;
+        Q.w = L.Rw;
+        Q.wod = omega / Q.d;
+        static bool attr2[2] = {false, false};
+        const bool hasn = Q.cN != 0.0;
+        size_t smem2 = ((size_t)Q.NS * (Q.XW + 8) + (size_t)3 * (Q.XW + 4)) * sizeof(double) + 8 * sizeof(uint64_t);
+        void (*kern)(const St2) = hasn ? k_jr2<true> : k_jr2<false>;
+        if (!attr2[hasn]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            attr2[hasn] = true;
+        }
+        dist_halo_wait(h);
+        kern<<<dim3(Q.XC, (Q.NY + Q.YL - 1) / Q.YL), ST2_NT, smem2, g.stream>>>(Q);
+        return true;
+    }
     if (!xi) return true;
     P.xi = xi;
     P.b = b;

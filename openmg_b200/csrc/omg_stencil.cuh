@@ -25,6 +25,6 @@ bool stencil_prolong_rb_sweep(omg_hierarchy *h, Level &L, Level &C, const double
 // one full two-colour sweep from the zero iterate, x never read (coarse levels of a cycle).  b == nullptr: probe
 bool stencil_rb_sweep0(omg_hierarchy *h, Level &L, const double *b, double *xo);
 // xo = xi + omega (b - A xi)/diag ; rc = R (b - A xo): last pre-smoothing sweep + restricted residual in one pass over x
-// (unsharded pure-band 3-D levels).  xi == nullptr: probe
+// (unsharded pure-band levels: k_jr3 in 3-D, k_jr2 in 2-D / 1-D).  xi == nullptr: probe
 bool stencil_jacobi_residual_restrict(omg_hierarchy *h, Level &L, Level &C, const double *xi, const double *b,
                                       double *xo, double *rc, double omega);

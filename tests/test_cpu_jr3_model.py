@@ -195,3 +195,104 @@ def test_jr3_model_matches_oracle(cfg):
     assert not np.isnan(rc).any(), "every coarse row is written exactly by its owner"
     assert np.abs(xo - xw).max() <= 1e-14
     assert np.abs(rc - rw).max() <= 1e-13
+
+
+def jr2_model(shape, XW, YL, NS=4, seed=0):
+    """`k_jr2`, the row-marching 2-D / 1-D member (x-chunks of XW columns of y-segments of YL rows, one halo pair per
+    side and one halo row per segment end recomputed, raw ring of NS rows, 3 mid rows); 1-D vectors are rows of N."""
+    oned = len(shape) == 1
+    A = sp.csr_matrix(orc.poisson_csr(shape, sparse_1d=oned))
+    n = A.shape[0]
+    if oned:
+        N = XW * 2 if n % (XW * 2) == 0 else XW       # view as rows of N
+    else:
+        N = shape[0]
+    NY = n // N
+    rs = np.random.RandomState(seed)
+    x, b = rs.random_sample(n), rs.random_sample(n)
+    omega = 0.8
+    i = 2 * N + 3 if not oned else 5
+    d = A[i, i]; c1 = A[i, i + 1]
+    cN = A[i, i + N] if not oned else 0.0
+    cD = A[i, i + N + 1] if not oned else 0.0
+    wod = omega / d
+    R = orc.restrictionList(shape, 1, 2)[0]
+    w = R.data[0]
+    pad = 2 * N + 8
+    X = np.zeros(n + 2 * pad); X[pad:pad + n] = x
+    B = np.zeros(n + 2 * pad); B[pad:pad + n] = b
+    XO = np.full(n, np.nan)
+    cs = N // 2
+    RC = np.full(R.shape[0], np.nan)
+    RP, MP = XW + 8, XW + 4
+    HXW, NPA, MPH = XW // 2, XW // 2 + 2, (XW + 4) // 2
+    ntot = NY * N
+    for by in range((NY + YL - 1) // YL):
+        for bx in range(N // XW):
+            x0, y0 = bx * XW, by * YL
+            y1 = min(y0 + YL, NY)
+            rlo, rhi, first = y0 - 2, y1 + 1, y0 - 1
+            raw = {}
+            def stage(r):
+                assert len(raw) < NS
+                raw[r] = X[pad + r * N + x0 - 4: pad + r * N + x0 - 4 + RP].copy()
+            for r in range(rlo, min(rlo + NS, rhi + 1)): stage(r)
+            mid = {}
+            bold = {}; acc = {}
+            for it in range(y0 - 1, y1 + 1):
+                sm, sc, spp = raw[it - 1], raw[it], raw[it + 1]
+                mw = np.full(MP, np.nan)
+                bvs = {}
+                for p in range(NPA):
+                    bv = B[pad + it * N + x0 - 2 + 2 * p: pad + it * N + x0 - 2 + 2 * p + 2].copy()
+                    bvs[p] = bv
+                    o = 2 + 2 * p; xg = x0 - 2 + 2 * p; gi = it * N + xg
+                    c = sc[o:o + 2].copy()
+                    if 0 <= gi < ntot:
+                        l, r_ = sc[o - 1], sc[o + 2]
+                        q = spp[o:o + 2]
+                        ml, m0, pr = sm[o - 1], sm[o], spp[o + 2]
+                        ax0 = d * c[0] + c1 * (l + c[1]) + cD * (ml + q[1])
+                        ax1 = d * c[1] + c1 * (c[0] + r_) + cD * (m0 + pr)
+                        if cN != 0.0:
+                            ax0 += cN * (m0 + q[0]); ax1 += cN * (sm[o + 1] + q[1])
+                        c = np.array([c[0] + wod * (bv[0] - ax0), c[1] + wod * (bv[1] - ax1)])
+                        if y0 <= it < y1 and 1 <= p <= HXW:
+                            XO[gi:gi + 2] = c
+                    mw[p] = c[0]; mw[MPH + p] = c[1]
+                mid[it] = mw
+                for k_ in list(mid):
+                    if k_ < it - 2: mid.pop(k_)
+                assert len(mid) <= 3
+                r = it - 1
+                if r >= y0:
+                    em, ec, ep = mid[r - 1], mid[r], mid[r + 1]
+                    om, oc, op = em[MPH:], ec[MPH:], ep[MPH:]
+                    close = oned or (r & 1)
+                    base = (r if oned else r >> 1) * cs + (x0 >> 1) - 1
+                    for p in range(1, HXW + 1):
+                        cx, cy = ec[p], oc[p]
+                        ax0 = d * cx + c1 * (oc[p - 1] + cy) + cD * (om[p - 1] + op[p])
+                        ax1 = d * cy + c1 * (cx + ec[p + 1]) + cD * (em[p] + ep[p + 1])
+                        if cN != 0.0:
+                            ax0 += cN * (em[p] + ep[p]); ax1 += cN * (om[p] + op[p])
+                        a = acc.get(p, 0.0) + ((bold[p][0] - ax0) + (bold[p][1] - ax1))
+                        if close:
+                            RC[base + p] = w * a; a = 0.0
+                        acc[p] = a
+                bold = bvs
+                rn = it - 1 + NS
+                if rn <= rhi:
+                    raw.pop(it - 1); stage(rn)
+    return A, R, x, b, omega, XO, RC
+
+
+@pytest.mark.parametrize("cfg", [((16, 16), 8, 4), ((16, 16), 16, 16), ((16, 16), 8, 6), ((32, 32), 8, 10, 5),
+                                 ((256,), 8, 4), ((256,), 16, 6), ((512,), 32, 16, 6)])
+def test_jr2_model_matches_oracle(cfg):
+    A, R, x, b, omega, xo, rc = jr2_model(*cfg)
+    xw = orc.jacobi(A, b, x.copy(), 1, omega)
+    rw = R.dot(b - A.dot(xw))
+    assert not np.isnan(rc).any() and not np.isnan(xo).any(), "every row is written exactly by its owner"
+    assert np.abs(xo - xw).max() <= 1e-14
+    assert np.abs(rc - rw).max() <= 1e-13

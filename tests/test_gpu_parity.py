@@ -248,7 +248,24 @@ def test_3d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, monkeypa
     one pass over x) against the oracle and against the two separate kernels (OMG_NO_JR3): first/last chunks and
     segments (flat-index wraps into the neighbouring planes), one and two patch slots per thread, 64- to 512-wide
     rows, with and without preceding sweeps."""
-    A0 = sp.csr_matrix(orc.poisson_csr(shape))
+    _single_pass_descent_case(shape, gl, monkeypatch)
+
+
+@pytest.mark.parametrize("shape,gl,maxw", [((256, 256), 3, None), ((1024, 1024), 5, None), ((1024, 1024), 5, 256),
+                                           ((2048, 2048), 6, 1024), ((1 << 15,), 3, None), ((1 << 20,), 8, None),
+                                           (((1 << 21) + 4096,), 10, 512)])
+def test_2d_1d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, maxw, monkeypatch):
+    """k_jr2, the row-marching member of the same family (2-D level 0: offsets 1 and N+1, openmg/operators.py:221-241;
+    1-D vectors viewed as rows of 2048), one and several x-chunks (OMG_RB_MAXW) and y-segments, row ends continuing
+    into the next row."""
+    if maxw:
+        monkeypatch.setenv("OMG_RB_MAXW", str(maxw))
+    _single_pass_descent_case(shape, gl, monkeypatch)
+
+
+def _single_pass_descent_case(shape, gl, monkeypatch):
+    s1 = len(shape) == 1
+    A0 = sp.csr_matrix(orc.poisson_csr(shape, sparse_1d=s1))
     R = orc.restrictionList(shape, gl - 1, 8)
     n = A0.shape[0]
     rs = np.random.RandomState(29)
@@ -259,7 +276,7 @@ def test_3d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, monkeypa
             monkeypatch.delenv("OMG_NO_JR3", raising=False)
         else:
             monkeypatch.setenv("OMG_NO_JR3", "1")
-        h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+        h = Hierarchy(omg.operators.poisson_band(shape, sparse_1d=s1), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
         outs[on] = [h.smooth_residual_restrict(0, b, x, sweeps, "jacobi", 0.8) for sweeps in (1, 2, 3)]
         outs[on].append(h.smooth_residual_restrict(0, b, np.zeros(n), 1, "jacobi", 0.8))
         h.close()
@@ -273,7 +290,7 @@ def test_3d_jacobi_sweep_and_restricted_residual_single_pass(shape, gl, monkeypa
     # small residuals: the patch-sum form of the residual must not lose accuracy when b - A x cancels
     xs = rs.random_sample(n)
     bs = A0.dot(xs)
-    h = Hierarchy(omg.operators.poisson_band(shape), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
+    h = Hierarchy(omg.operators.poisson_band(shape, sparse_1d=s1), shape, gl - 1, 8, flags=_lib.FLAG_NO_GRAPH)
     xg, rg = h.smooth_residual_restrict(0, bs, xs, 1, "jacobi", 0.8)
     h.close()
     close(xg, xs, 1e-14, "x already solves A x = b: the sweep leaves it alone")
