@@ -4,9 +4,11 @@ into one row per launch of the LAST V-cycle in the log: kernel, grid, block, tim
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -k regex:'^k_(st|fix|coarse_gemv|jacobi|residual|prolong|colour)' --csv --log-file gpurun_out/launches.csv \
         python tools/gpu_probe.py --cycles 2
-    python tools/ncu_launches.py gpurun_out/launches.csv 2 > profiles/<name>.csv \
+    python tools/ncu_launches.py gpurun_out/launches.csv 4 > profiles/<name>.csv \
         [--traffic profiles/traffic.json --shape 512x512x512 --smoother jacobi|rbgs]
 
+The second argument is the number of V-cycles in the log: `gpu_probe.py --cycles 2` runs two warm-up cycles (one per
+ping-pong parity, omg_bench_cycles) and the two timed ones, so 4; the last cycle is the one condensed.
 Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py, not absolutes.
 """
 import csv
