@@ -179,7 +179,8 @@ int launch_residual_restrict(omg_hierarchy *h, int l, double *x, const double *b
 
 // pre-smoothing + restricted residual (openmg/__init__.py:201, :209-210): `sweeps` sweeps from *cur (nullptr = zero
 // iterate), then b_{l+1} = R_l (b_l - A_l x).  A last Jacobi sweep from a non-zero iterate and the restricted residual
-// run as ONE pass over x where the level allows it (k_jr3).  *cur: the buffer holding the smoothed iterate.
+// run as ONE pass over x where the level allows it (k_jr3 / k_jr2: unsharded levels only, so no halo is involved).
+// *cur: the buffer holding the smoothed iterate.
 int launch_smooth_residual_restrict(omg_hierarchy *h, int l, int smoother, double omega, int sweeps, double **cur,
                                     const double *b, double *rc) {
     Level &L = h->lv[l];
@@ -333,7 +334,8 @@ static double *cycle_level(omg_hierarchy *h, int l, const CycleCfg &cfg, double 
     }
     if (!fused0) launch_smooth_residual_restrict(h, l, cfg.smoother, cfg.omega, cfg.pre, &cur, L.b, C.b);
     double *e = cycle_level(h, l + 1, cfg, nullptr);
-    // cur's halos were filled for the restriction (unfused path) and cur has not changed since
+    // cur's halos were filled for the restriction (unfused path) and cur has not changed since (the single-pass descent
+    // kernels only run on unsharded levels, which have no halos)
     return launch_prolong_correct_smooth(h, l, cfg.smoother, cfg.omega, cfg.post, cur, e, L.b, !fused0);
 }
 
